@@ -1,0 +1,888 @@
+// Host side of the C-ABI declared in include/b200coll.h: arena creation and sharing (VMM + POSIX fd,
+// or legacy CUDA IPC), NVSwitch multicast binding, algorithm selection and kernel launches.
+//
+// The driver API (cuMem*, cuMulticast*) is reached through cudaGetDriverEntryPoint so the library
+// has no link-time dependency on libcuda and can be loaded (symbol check) on a machine without a GPU.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "byte_kernels.cuh"
+#include "launch_typed.cuh"
+
+using namespace b200c;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define RT(x)                                                                                      \
+  do {                                                                                             \
+    cudaError_t e_ = (x);                                                                          \
+    if (e_ != cudaSuccess) return fail(B200C_ECUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); \
+  } while (0)
+
+static std::atomic<uint64_t> g_launches{0};
+
+// ------------------------------------------------------------------------------------------------
+// driver entry points
+// ------------------------------------------------------------------------------------------------
+struct Driver {
+  bool ok = false;
+  CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+  CUresult (*DeviceGetAttribute)(int*, CUdevice_attribute, CUdevice) = nullptr;
+  CUresult (*MemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*MemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*MemExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+  CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
+  CUresult (*MulticastCreate)(CUmemGenericAllocationHandle*, const CUmulticastObjectProp*) = nullptr;
+  CUresult (*MulticastAddDevice)(CUmemGenericAllocationHandle, CUdevice) = nullptr;
+  CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long) = nullptr;
+  CUresult (*MulticastUnbind)(CUmemGenericAllocationHandle, CUdevice, size_t, size_t) = nullptr;
+  CUresult (*MulticastGetGranularity)(size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags) = nullptr;
+};
+static Driver g_drv;
+static std::once_flag g_drv_once;
+
+template <typename F>
+static bool load_sym(const char* name, F* out) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+    cudaGetLastError();
+    return false;
+  }
+  *out = reinterpret_cast<F>(p);
+  return true;
+}
+static void load_driver() {
+  Driver& d = g_drv;
+  bool ok = true;
+  ok &= load_sym("cuGetErrorString", &d.GetErrorString);
+  ok &= load_sym("cuDeviceGet", &d.DeviceGet);
+  ok &= load_sym("cuDeviceGetAttribute", &d.DeviceGetAttribute);
+  ok &= load_sym("cuMemGetAllocationGranularity", &d.MemGetAllocationGranularity);
+  ok &= load_sym("cuMemCreate", &d.MemCreate);
+  ok &= load_sym("cuMemRelease", &d.MemRelease);
+  ok &= load_sym("cuMemAddressReserve", &d.MemAddressReserve);
+  ok &= load_sym("cuMemAddressFree", &d.MemAddressFree);
+  ok &= load_sym("cuMemMap", &d.MemMap);
+  ok &= load_sym("cuMemUnmap", &d.MemUnmap);
+  ok &= load_sym("cuMemSetAccess", &d.MemSetAccess);
+  ok &= load_sym("cuMemExportToShareableHandle", &d.MemExportToShareableHandle);
+  ok &= load_sym("cuMemImportFromShareableHandle", &d.MemImportFromShareableHandle);
+  // multicast is optional
+  load_sym("cuMulticastCreate", &d.MulticastCreate);
+  load_sym("cuMulticastAddDevice", &d.MulticastAddDevice);
+  load_sym("cuMulticastBindMem", &d.MulticastBindMem);
+  load_sym("cuMulticastUnbind", &d.MulticastUnbind);
+  load_sym("cuMulticastGetGranularity", &d.MulticastGetGranularity);
+  d.ok = ok;
+}
+static const char* cu_str(CUresult r) {
+  const char* s = nullptr;
+  if (g_drv.GetErrorString) g_drv.GetErrorString(r, &s);
+  return s ? s : "unknown";
+}
+#define DRV(call)                                                                                   \
+  do {                                                                                              \
+    CUresult r_ = (call);                                                                           \
+    if (r_ != CUDA_SUCCESS) return fail(B200C_ECUDA, "%s failed: %d (%s)", #call, (int)r_, cu_str(r_)); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1, dev;
+  bool switched = false;
+  explicit DeviceGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != d) { cudaSetDevice(d); switched = true; }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// communicator
+// ------------------------------------------------------------------------------------------------
+struct b200c_comm {
+  int rank = 0, world = 1, device = 0;
+  CUdevice cudev = 0;
+  b200c_config_t cfg{};
+  int sm_count = 148;
+  // arena
+  size_t arena_bytes = 0, gran = 0;
+  size_t off_staging = 0, off_p2p = 0, off_sym = 0, sym_bytes = 0;
+  uint64_t layout_hash = 0;
+  bool vmm = true;
+  CUmemGenericAllocationHandle own_handle = 0;
+  CUmemGenericAllocationHandle peer_handle[kMaxRanks] = {};
+  char* arena[kMaxRanks] = {};
+  bool imported[kMaxRanks] = {};
+  // multicast
+  CUmemGenericAllocationHandle mc_handle = 0;
+  bool mc_have_handle = false, mc_added = false, mc_bound = false;
+  char* mc_arena = nullptr;
+  // status
+  Status* status_host = nullptr;
+  Status* status_dev = nullptr;
+  // state
+  bool ready = false, destroyed = false;
+  uint32_t seq = 0;
+  uint32_t send_cells[kMaxRanks] = {};
+  uint32_t recv_cells[kMaxRanks] = {};
+  DevComm dev{};
+};
+
+static size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int b200c_version(void) { return B200C_VERSION; }
+extern "C" const char* b200c_last_error(void) { return g_err; }
+extern "C" const char* b200c_status_string(int s) {
+  switch (s) {
+    case B200C_OK: return "ok";
+    case B200C_EINVAL: return "invalid argument";
+    case B200C_ECUDA: return "CUDA error";
+    case B200C_ESTATE: return "communicator not ready or destroyed";
+    case B200C_EUNSUPPORTED: return "unsupported dtype/op/algorithm";
+    case B200C_ETIMEOUT: return "timed out waiting for a peer";
+    case B200C_EABORTED: return "communicator aborted";
+    case B200C_EMISMATCH: return "peers disagree on the collective's arguments";
+    case B200C_ENOMEM: return "out of memory";
+    default: return "unknown status";
+  }
+}
+extern "C" size_t b200c_dtype_size(int dtype) {
+  switch (dtype) {
+    case B200C_INT8: case B200C_UINT8: return 1;
+    case B200C_FLOAT16: case B200C_BFLOAT16: return 2;
+    case B200C_INT32: case B200C_UINT32: case B200C_FLOAT32: return 4;
+    case B200C_INT64: case B200C_UINT64: case B200C_FLOAT64: return 8;
+    default: return 0;
+  }
+}
+extern "C" uint64_t b200c_launch_count(void) { return g_launches.load(); }
+
+extern "C" void b200c_default_config(b200c_config_t* cfg) {
+  memset(cfg, 0, sizeof *cfg);
+  cfg->struct_size = sizeof *cfg;
+  cfg->share_mode = B200C_SHARE_VMM_FD;
+  cfg->staging_bytes = 256ull << 20;
+  cfg->symmetric_bytes = 0;
+  cfg->p2p_slot_bytes = 32ull << 10;
+  cfg->p2p_slots = 256;
+  cfg->max_blocks = 296;
+  cfg->oneshot_max_bytes = 0;  // 0 = pick by world size in b200c_comm_create
+  cfg->nvls_min_bytes = 1ull << 20;
+  cfg->timeout_ms = 30000;
+}
+
+static int ensure_driver() {
+  std::call_once(g_drv_once, load_driver);
+  if (!g_drv.ok) return fail(B200C_ECUDA, "CUDA driver entry points unavailable (no GPU driver?)");
+  return B200C_OK;
+}
+
+extern "C" int b200c_device_props(int device, b200c_props_t* out) {
+  if (!out) return fail(B200C_EINVAL, "out is null");
+  memset(out, 0, sizeof *out);
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+    cudaGetLastError();
+    return fail(B200C_ECUDA, "no CUDA device %d (count %d)", device, n);
+  }
+  int rc = ensure_driver();
+  if (rc) return rc;
+  cudaDeviceProp p;
+  RT(cudaGetDeviceProperties(&p, device));
+  out->device = device;
+  out->sm_count = p.multiProcessorCount;
+  out->cc_major = p.major;
+  out->cc_minor = p.minor;
+  out->total_mem = p.totalGlobalMem;
+  DeviceGuard g(device);
+  RT(cudaFree(0));
+  CUdevice cd;
+  DRV(g_drv.DeviceGet(&cd, device));
+  g_drv.DeviceGetAttribute(&out->vmm_supported, CU_DEVICE_ATTRIBUTE_VIRTUAL_MEMORY_MANAGEMENT_SUPPORTED, cd);
+  g_drv.DeviceGetAttribute(&out->posix_fd_supported, CU_DEVICE_ATTRIBUTE_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR_SUPPORTED, cd);
+  g_drv.DeviceGetAttribute(&out->multicast_supported, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, cd);
+  return B200C_OK;
+}
+
+static CUmemAllocationProp alloc_prop(CUdevice cd) {
+  CUmemAllocationProp ap;
+  memset(&ap, 0, sizeof ap);
+  ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  ap.location.id = cd;
+  ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  return ap;
+}
+static int map_handle(b200c_comm* c, CUmemGenericAllocationHandle h, char** out) {
+  CUdeviceptr va = 0;
+  DRV(g_drv.MemAddressReserve(&va, c->arena_bytes, c->gran, 0, 0));
+  CUresult r = g_drv.MemMap(va, c->arena_bytes, 0, h, 0);
+  if (r != CUDA_SUCCESS) { g_drv.MemAddressFree(va, c->arena_bytes); return fail(B200C_ECUDA, "cuMemMap failed: %d (%s)", (int)r, cu_str(r)); }
+  CUmemAccessDesc ad;
+  memset(&ad, 0, sizeof ad);
+  ad.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  ad.location.id = c->cudev;
+  ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  r = g_drv.MemSetAccess(va, c->arena_bytes, &ad, 1);
+  if (r != CUDA_SUCCESS) { g_drv.MemUnmap(va, c->arena_bytes); g_drv.MemAddressFree(va, c->arena_bytes); return fail(B200C_ECUDA, "cuMemSetAccess failed: %d (%s)", (int)r, cu_str(r)); }
+  *out = reinterpret_cast<char*>(va);
+  return B200C_OK;
+}
+
+extern "C" int b200c_comm_create(int rank, int world, int device, const b200c_config_t* cfg_in, b200c_comm_t** out) {
+  if (!out) return fail(B200C_EINVAL, "out is null");
+  if (world < 1 || world > kMaxRanks) return fail(B200C_EINVAL, "world size %d not in [1, %d] (one NVSwitch domain)", world, kMaxRanks);
+  if (rank < 0 || rank >= world) return fail(B200C_EINVAL, "rank %d not in [0, %d)", rank, world);
+  int rc = ensure_driver();
+  if (rc) return rc;
+  b200c_config_t cfg;
+  b200c_default_config(&cfg);
+  if (cfg_in) {
+    if (cfg_in->struct_size != sizeof(b200c_config_t)) return fail(B200C_EINVAL, "config struct_size %u != %zu", cfg_in->struct_size, sizeof(b200c_config_t));
+    cfg = *cfg_in;
+  }
+  if (cfg.max_blocks == 0 || cfg.max_blocks > (uint32_t)kMaxBlocks) return fail(B200C_EINVAL, "max_blocks %u not in [1, %d]", cfg.max_blocks, kMaxBlocks);
+  if (cfg.p2p_slots == 0 || cfg.p2p_slots > (uint32_t)kMaxCells) return fail(B200C_EINVAL, "p2p_slots %u not in [1, %d]", cfg.p2p_slots, kMaxCells);
+  if (cfg.p2p_slot_bytes < 512 || cfg.p2p_slot_bytes % 16) return fail(B200C_EINVAL, "p2p_slot_bytes must be a multiple of 16 and >= 512");
+  if (cfg.staging_bytes < (1u << 16) || cfg.staging_bytes % 4096) return fail(B200C_EINVAL, "staging_bytes must be a multiple of 4096 and >= 64 KiB");
+  if (cfg.timeout_ms == 0) cfg.timeout_ms = 30000;
+  if (cfg.oneshot_max_bytes == 0) cfg.oneshot_max_bytes = world <= 2 ? (8ull << 20) : (world <= 4 ? (512ull << 10) : (256ull << 10));
+
+  int ndev = 0;
+  RT(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(B200C_EINVAL, "device %d not visible (count %d)", device, ndev);
+  DeviceGuard g(device);
+  RT(cudaFree(0));
+  b200c_comm* c = new b200c_comm();
+  c->rank = rank; c->world = world; c->device = device; c->cfg = cfg;
+  c->vmm = cfg.share_mode == B200C_SHARE_VMM_FD;
+  cudaDeviceProp prop;
+  RT(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  DRV(g_drv.DeviceGet(&c->cudev, device));
+
+  // layout
+  c->off_staging = kPadBytes;
+  c->off_p2p = c->off_staging + 2 * cfg.staging_bytes;
+  size_t p2p_bytes = world > 1 ? (size_t)kMaxRanks * cfg.p2p_slots * cfg.p2p_slot_bytes : 0;
+  c->off_sym = round_up(c->off_p2p + p2p_bytes, 2ull << 20);
+  size_t want = c->off_sym + cfg.symmetric_bytes;
+  size_t gran = 2ull << 20;
+  if (c->vmm) {
+    CUmemAllocationProp ap = alloc_prop(c->cudev);
+    size_t g1 = 0;
+    DRV(g_drv.MemGetAllocationGranularity(&g1, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+    if (g1 > gran) gran = g1;
+    int mc = 0;
+    g_drv.DeviceGetAttribute(&mc, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, c->cudev);
+    if (mc && g_drv.MulticastGetGranularity && world > 1) {
+      CUmulticastObjectProp mp;
+      memset(&mp, 0, sizeof mp);
+      mp.numDevices = world; mp.size = round_up(want, gran); mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+      size_t g2 = 0;
+      if (g_drv.MulticastGetGranularity(&g2, &mp, CU_MULTICAST_GRANULARITY_MINIMUM) == CUDA_SUCCESS && g2 > gran) gran = g2;
+    }
+  }
+  c->gran = gran;
+  c->arena_bytes = round_up(want, gran);
+  c->sym_bytes = c->arena_bytes - c->off_sym;
+  c->layout_hash = (uint64_t)cfg.staging_bytes * 1000003ull ^ (uint64_t)cfg.p2p_slot_bytes * 10007ull ^ (uint64_t)cfg.p2p_slots * 101ull ^
+                   (uint64_t)c->arena_bytes ^ ((uint64_t)cfg.max_blocks << 48) ^ ((uint64_t)world << 56);
+
+  if (c->vmm) {
+    CUmemAllocationProp ap = alloc_prop(c->cudev);
+    CUresult r = g_drv.MemCreate(&c->own_handle, c->arena_bytes, &ap, 0);
+    if (r != CUDA_SUCCESS) { size_t ab = c->arena_bytes; delete c; return fail(r == CUDA_ERROR_OUT_OF_MEMORY ? B200C_ENOMEM : B200C_ECUDA, "cuMemCreate(%zu bytes) failed: %d (%s)", ab, (int)r, cu_str(r)); }
+    rc = map_handle(c, c->own_handle, &c->arena[rank]);
+    if (rc) { g_drv.MemRelease(c->own_handle); delete c; return rc; }
+  } else {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, c->arena_bytes);
+    if (e != cudaSuccess) { size_t ab = c->arena_bytes; delete c; return fail(e == cudaErrorMemoryAllocation ? B200C_ENOMEM : B200C_ECUDA, "cudaMalloc(%zu) failed: %s", ab, cudaGetErrorString(e)); }
+    c->arena[rank] = static_cast<char*>(p);
+  }
+  c->imported[rank] = true;
+  RT(cudaMemset(c->arena[rank], 0, kPadBytes));
+  RT(cudaHostAlloc(reinterpret_cast<void**>(&c->status_host), sizeof(Status), cudaHostAllocMapped | cudaHostAllocPortable));
+  memset((void*)c->status_host, 0, sizeof(Status));
+  RT(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->status_dev), (void*)c->status_host, 0));
+  RT(cudaDeviceSynchronize());
+  *out = c;
+  return B200C_OK;
+}
+
+extern "C" int b200c_comm_export(b200c_comm_t* c, b200c_export_t* out) {
+  if (!c || !out) return fail(B200C_EINVAL, "null argument");
+  if (c->destroyed) return fail(B200C_ESTATE, "communicator destroyed");
+  memset(out, 0, sizeof *out);
+  out->share_mode = c->vmm ? B200C_SHARE_VMM_FD : B200C_SHARE_LEGACY_IPC;
+  out->fd = -1;
+  out->arena_bytes = c->arena_bytes;
+  out->layout_hash = c->layout_hash;
+  out->pid = (int32_t)getpid();
+  DeviceGuard g(c->device);
+  if (c->vmm) {
+    int fd = -1;
+    DRV(g_drv.MemExportToShareableHandle(&fd, c->own_handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+    out->fd = fd;
+  } else {
+    cudaIpcMemHandle_t h;
+    RT(cudaIpcGetMemHandle(&h, c->arena[c->rank]));
+    static_assert(sizeof h == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(out->ipc, &h, 64);
+  }
+  return B200C_OK;
+}
+
+extern "C" int b200c_comm_import(b200c_comm_t* c, int peer, const b200c_export_t* e) {
+  if (!c || !e) return fail(B200C_EINVAL, "null argument");
+  if (c->destroyed) return fail(B200C_ESTATE, "communicator destroyed");
+  if (peer < 0 || peer >= c->world || peer == c->rank) return fail(B200C_EINVAL, "bad peer %d", peer);
+  if (c->imported[peer]) return fail(B200C_ESTATE, "peer %d already imported", peer);
+  if (e->arena_bytes != c->arena_bytes || e->layout_hash != c->layout_hash)
+    return fail(B200C_EMISMATCH, "peer %d arena layout differs (bytes %llu vs %zu): all ranks must use the same config", peer,
+                (unsigned long long)e->arena_bytes, c->arena_bytes);
+  if ((e->share_mode == B200C_SHARE_VMM_FD) != c->vmm) return fail(B200C_EMISMATCH, "peer %d uses a different share mode", peer);
+  DeviceGuard g(c->device);
+  if (c->vmm) {
+    if (e->fd < 0) return fail(B200C_EINVAL, "peer %d export carries no fd", peer);
+    DRV(g_drv.MemImportFromShareableHandle(&c->peer_handle[peer], (void*)(uintptr_t)e->fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+    int rc = map_handle(c, c->peer_handle[peer], &c->arena[peer]);
+    if (rc) return rc;
+  } else {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, e->ipc, 64);
+    void* p = nullptr;
+    RT(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->arena[peer] = static_cast<char*>(p);
+  }
+  c->imported[peer] = true;
+  return B200C_OK;
+}
+
+extern "C" int b200c_comm_mc_create(b200c_comm_t* c, int* fd_out) {
+  if (!c || !fd_out) return fail(B200C_EINVAL, "null argument");
+  if (!c->vmm) return fail(B200C_EUNSUPPORTED, "multicast needs the VMM share mode");
+  if (!g_drv.MulticastCreate) return fail(B200C_EUNSUPPORTED, "driver has no cuMulticastCreate");
+  int mc = 0;
+  g_drv.DeviceGetAttribute(&mc, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, c->cudev);
+  if (!mc) return fail(B200C_EUNSUPPORTED, "device does not support multicast");
+  DeviceGuard g(c->device);
+  CUmulticastObjectProp mp;
+  memset(&mp, 0, sizeof mp);
+  mp.numDevices = c->world; mp.size = c->arena_bytes; mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  DRV(g_drv.MulticastCreate(&c->mc_handle, &mp));
+  c->mc_have_handle = true;
+  int fd = -1;
+  DRV(g_drv.MemExportToShareableHandle(&fd, c->mc_handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+  *fd_out = fd;
+  return B200C_OK;
+}
+extern "C" int b200c_comm_mc_import(b200c_comm_t* c, int fd) {
+  if (!c || fd < 0) return fail(B200C_EINVAL, "bad argument");
+  if (!c->vmm) return fail(B200C_EUNSUPPORTED, "multicast needs the VMM share mode");
+  DeviceGuard g(c->device);
+  DRV(g_drv.MemImportFromShareableHandle(&c->mc_handle, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+  c->mc_have_handle = true;
+  return B200C_OK;
+}
+extern "C" int b200c_comm_mc_add_device(b200c_comm_t* c) {
+  if (!c || !c->mc_have_handle) return fail(B200C_ESTATE, "no multicast handle");
+  DeviceGuard g(c->device);
+  DRV(g_drv.MulticastAddDevice(c->mc_handle, c->cudev));
+  c->mc_added = true;
+  return B200C_OK;
+}
+extern "C" int b200c_comm_mc_bind(b200c_comm_t* c) {
+  if (!c || !c->mc_added) return fail(B200C_ESTATE, "device not added to the multicast object");
+  DeviceGuard g(c->device);
+  DRV(g_drv.MulticastBindMem(c->mc_handle, 0, c->own_handle, 0, c->arena_bytes, 0));
+  c->mc_bound = true;
+  int rc = map_handle(c, c->mc_handle, &c->mc_arena);
+  if (rc) { c->mc_arena = nullptr; return rc; }
+  return B200C_OK;
+}
+
+extern "C" int b200c_comm_mc_disable(b200c_comm_t* c) {
+  if (!c) return fail(B200C_EINVAL, "null communicator");
+  DeviceGuard g(c->device);
+  if (c->mc_arena) { g_drv.MemUnmap((CUdeviceptr)c->mc_arena, c->arena_bytes); g_drv.MemAddressFree((CUdeviceptr)c->mc_arena, c->arena_bytes); c->mc_arena = nullptr; }
+  if (c->ready) c->dev.mc_arena = nullptr;
+  return B200C_OK;
+}
+
+extern "C" int b200c_comm_ready(b200c_comm_t* c) {
+  if (!c) return fail(B200C_EINVAL, "null communicator");
+  if (c->destroyed) return fail(B200C_ESTATE, "communicator destroyed");
+  for (int j = 0; j < c->world; j++)
+    if (!c->imported[j]) return fail(B200C_ESTATE, "peer %d not imported yet", j);
+  DevComm& d = c->dev;
+  memset(&d, 0, sizeof d);
+  d.rank = c->rank; d.world = c->world;
+  for (int j = 0; j < c->world; j++) d.arena[j] = c->arena[j];
+  d.mc_arena = c->mc_arena;
+  d.status = c->status_dev;
+  d.timeout_ns = (unsigned long long)c->cfg.timeout_ms * 1000000ull;
+  d.staging_bytes = c->cfg.staging_bytes;
+  d.off_staging = c->off_staging;
+  d.off_p2p = c->off_p2p;
+  d.p2p_cell_bytes = c->cfg.p2p_slot_bytes;
+  d.p2p_cells = (int)c->cfg.p2p_slots;
+  c->ready = true;
+  return B200C_OK;
+}
+
+extern "C" int b200c_comm_abort(b200c_comm_t* c) {
+  if (!c) return fail(B200C_EINVAL, "null communicator");
+  if (c->status_host) c->status_host->abort_flag = 1;
+  return B200C_OK;
+}
+
+extern "C" int b200c_comm_check(b200c_comm_t* c) {
+  if (!c) return fail(B200C_EINVAL, "null communicator");
+  if (!c->status_host) return B200C_OK;
+  int e = c->status_host->error;
+  if (e == 0) return B200C_OK;
+  static const char* phases[] = {"arrive", "flagA", "flagB", "p2p-ready", "p2p-ack"};
+  int ph = c->status_host->err_phase;
+  return fail(e, "%s: rank %d, op seq %u, waiting on peer %d (%s)", b200c_status_string(e), c->rank, c->status_host->err_seq,
+              c->status_host->err_peer, ph >= 0 && ph < 5 ? phases[ph] : "?");
+}
+
+extern "C" int b200c_comm_destroy(b200c_comm_t* c) {
+  if (!c) return B200C_OK;
+  if (c->destroyed) return B200C_OK;
+  c->destroyed = true;
+  c->ready = false;
+  if (c->status_host) c->status_host->abort_flag = 1;
+  DeviceGuard g(c->device);
+  cudaDeviceSynchronize();
+  cudaGetLastError();
+  if (c->vmm) {
+    if (c->mc_arena) { g_drv.MemUnmap((CUdeviceptr)c->mc_arena, c->arena_bytes); g_drv.MemAddressFree((CUdeviceptr)c->mc_arena, c->arena_bytes); }
+    if (c->mc_bound && g_drv.MulticastUnbind) g_drv.MulticastUnbind(c->mc_handle, c->cudev, 0, c->arena_bytes);
+    if (c->mc_have_handle) g_drv.MemRelease(c->mc_handle);
+    for (int j = 0; j < c->world; j++) {
+      if (!c->arena[j]) continue;
+      g_drv.MemUnmap((CUdeviceptr)c->arena[j], c->arena_bytes);
+      g_drv.MemAddressFree((CUdeviceptr)c->arena[j], c->arena_bytes);
+      if (j != c->rank && c->peer_handle[j]) g_drv.MemRelease(c->peer_handle[j]);
+    }
+    if (c->own_handle) g_drv.MemRelease(c->own_handle);
+  } else {
+    for (int j = 0; j < c->world; j++) {
+      if (!c->arena[j]) continue;
+      if (j == c->rank) cudaFree(c->arena[j]);
+      else cudaIpcCloseMemHandle(c->arena[j]);
+    }
+  }
+  if (c->status_host) cudaFreeHost((void*)c->status_host);
+  c->status_host = nullptr;
+  cudaGetLastError();
+  delete c;
+  return B200C_OK;
+}
+
+extern "C" int b200c_comm_rank(const b200c_comm_t* c) { return c ? c->rank : -1; }
+extern "C" int b200c_comm_world(const b200c_comm_t* c) { return c ? c->world : -1; }
+extern "C" int b200c_comm_has_multicast(const b200c_comm_t* c) { return c && c->mc_arena ? 1 : 0; }
+extern "C" uint64_t b200c_comm_seq(const b200c_comm_t* c) { return c ? c->seq : 0; }
+extern "C" void* b200c_comm_symmetric_base(b200c_comm_t* c) { return c && c->sym_bytes ? c->arena[c->rank] + c->off_sym : nullptr; }
+extern "C" uint64_t b200c_comm_symmetric_bytes(const b200c_comm_t* c) { return c ? c->sym_bytes : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// launch planning
+// ------------------------------------------------------------------------------------------------
+static int check_ready(b200c_comm* c) {
+  if (!c) return fail(B200C_EINVAL, "null communicator");
+  if (c->destroyed || !c->ready) return fail(B200C_ESTATE, "communicator not ready or destroyed");
+  if (c->status_host->error) return b200c_comm_check(c);
+  return B200C_OK;
+}
+static int launch_check(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(B200C_ECUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  return B200C_OK;
+}
+// split `units` elements (vector width vec) over blocks of at least min_tile_bytes
+static void plan_tiles(size_t units, size_t elem_size, size_t vec, uint32_t max_blocks, size_t min_tile_bytes, size_t* tile, int* grid) {
+  if (units == 0) { *tile = vec; *grid = 1; return; }
+  size_t bytes = units * elem_size;
+  size_t nb = (bytes + min_tile_bytes - 1) / min_tile_bytes;
+  if (nb < 1) nb = 1;
+  if (nb > max_blocks) nb = max_blocks;
+  size_t t = round_up((units + nb - 1) / nb, vec);
+  *tile = t;
+  *grid = (int)((units + t - 1) / t);
+}
+static uint32_t make_sig(int opcode, int dtype, int op, size_t n, int root, int extra) {
+  uint64_t h = 1469598103934665603ull;
+  uint64_t v[6] = {(uint64_t)opcode, (uint64_t)dtype, (uint64_t)op, (uint64_t)n, (uint64_t)(root + 1), (uint64_t)extra};
+  for (int i = 0; i < 6; i++) { h ^= v[i]; h *= 1099511628211ull; }
+  return (uint32_t)(h ^ (h >> 32)) | 1u;
+}
+static void base_args(b200c_comm* c, CollArgs* a) {
+  memset(a, 0, sizeof *a);
+  a->c = c->dev;
+  a->seq = ++c->seq;
+  a->root = -1;
+}
+static int launch_same_type(int dtype, int kind, int op, const CollArgs& a, int grid, cudaStream_t s) {
+  switch (dtype) {
+    case B200C_INT8: return launch_i8(kind, op, a, grid, s);
+    case B200C_UINT8: return launch_u8(kind, op, a, grid, s);
+    case B200C_INT32: return launch_i32(kind, op, a, grid, s);
+    case B200C_UINT32: return launch_u32(kind, op, a, grid, s);
+    case B200C_INT64: return launch_i64(kind, op, a, grid, s);
+    case B200C_UINT64: return launch_u64(kind, op, a, grid, s);
+    case B200C_FLOAT16: return launch_f16(kind, op, a, grid, s);
+    case B200C_FLOAT32: return launch_f32(kind, op, a, grid, s);
+    case B200C_FLOAT64: return launch_f64(kind, op, a, grid, s);
+    case B200C_BFLOAT16: return launch_bf16(kind, op, a, grid, s);
+    default: return fail(B200C_EUNSUPPORTED, "dtype %d", dtype);
+  }
+}
+
+enum { OPC_ALLREDUCE = 1, OPC_REDUCE, OPC_BROADCAST, OPC_ALLGATHER, OPC_REDUCESCATTER, OPC_BARRIER };
+constexpr size_t kMinTileBytes = 8192;
+
+// mixed-type (bucket dtype != wire dtype) and NVLS launches live in this TU
+template <typename TI, typename TW>
+static void launch_mixed(int algo, const CollArgs& a, int grid, cudaStream_t s) {
+  if (algo == B200C_ALGO_ONESHOT) k_allreduce_oneshot<TI, TW, B200C_SUM><<<grid, kThreads, 0, s>>>(a);
+  else k_allreduce_twoshot<TI, TW, B200C_SUM><<<grid, kThreads, 0, s>>>(a);
+}
+template <typename TI, typename TW>
+static void launch_nvls(const CollArgs& a, int grid, cudaStream_t s) {
+  k_allreduce_nvls<TI, TW><<<grid, kThreads, 0, s>>>(a);
+}
+
+static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t count, int dtype, int wire, int op, float scale,
+                          int has_scale, int algo, cudaStream_t s) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  size_t esz = b200c_dtype_size(dtype), wsz = b200c_dtype_size(wire);
+  if (!esz || !wsz) return fail(B200C_EINVAL, "bad dtype %d / wire %d", dtype, wire);
+  if (op < 0 || op >= B200C_NUM_OPS) return fail(B200C_EINVAL, "bad reduce op %d", op);
+  if (count && (!send || !recv)) return fail(B200C_EINVAL, "null buffer");
+  if (wire != dtype) {
+    if (!(dtype == B200C_FLOAT32 && (wire == B200C_BFLOAT16 || wire == B200C_FLOAT16))) return fail(B200C_EUNSUPPORTED, "wire dtype %d for buffer dtype %d", wire, dtype);
+    if (op != B200C_SUM && op != B200C_AVG) return fail(B200C_EUNSUPPORTED, "compressed wire supports SUM/AVG only");
+  }
+  if (algo < B200C_ALGO_AUTO || algo > B200C_ALGO_NVLS) return fail(B200C_EINVAL, "bad algo %d", algo);
+  if (op == B200C_AVG) { has_scale = 1; scale = 1.f / (float)c->world; }
+  if (count == 0) return B200C_OK;
+  DeviceGuard g(c->device);
+  const int W = c->world;
+  const size_t vec = 16 / wsz;
+  if (W == 1) {
+    if (send == recv && !has_scale && wire == dtype) return B200C_OK;
+    if (!has_scale && wire == dtype) { RT(cudaMemcpyAsync(recv, send, count * esz, cudaMemcpyDeviceToDevice, s)); return B200C_OK; }
+    CollArgs a; memset(&a, 0, sizeof a);
+    a.c = c->dev; a.in = send; a.out = recv; a.n = count; a.has_scale = has_scale; a.scale = scale;
+    int grid; plan_tiles(count, esz, vec, c->cfg.max_blocks * 4 > 1024 ? 1024 : c->cfg.max_blocks * 4, kMinTileBytes, &a.tile, &grid);
+    switch (dtype * 16 + wire) {
+      case B200C_FLOAT32 * 16 + B200C_FLOAT32: k_local_scale<float, float><<<grid, kThreads, 0, s>>>(a); break;
+      case B200C_FLOAT32 * 16 + B200C_BFLOAT16: k_local_scale<float, bf16_t><<<grid, kThreads, 0, s>>>(a); break;
+      case B200C_FLOAT32 * 16 + B200C_FLOAT16: k_local_scale<float, f16_t><<<grid, kThreads, 0, s>>>(a); break;
+      case B200C_BFLOAT16 * 16 + B200C_BFLOAT16: k_local_scale<bf16_t, bf16_t><<<grid, kThreads, 0, s>>>(a); break;
+      case B200C_FLOAT16 * 16 + B200C_FLOAT16: k_local_scale<f16_t, f16_t><<<grid, kThreads, 0, s>>>(a); break;
+      case B200C_FLOAT64 * 16 + B200C_FLOAT64: k_local_scale<double, double><<<grid, kThreads, 0, s>>>(a); break;
+      default:
+        // integer AVG over one rank is the identity
+        if (send != recv) RT(cudaMemcpyAsync(recv, send, count * esz, cudaMemcpyDeviceToDevice, s));
+        return B200C_OK;
+    }
+    return launch_check("local_scale");
+  }
+
+  const bool nvls_ok = c->mc_arena && (op == B200C_SUM || op == B200C_AVG) &&
+                       (wire == B200C_FLOAT32 || wire == B200C_BFLOAT16 || wire == B200C_FLOAT16);
+  if (algo == B200C_ALGO_NVLS && !nvls_ok) return fail(B200C_EUNSUPPORTED, "NVLS needs a bound multicast object, SUM/AVG and f32/bf16/f16");
+  const char* in = static_cast<const char*>(send);
+  char* out = static_cast<char*>(recv);
+  size_t done = 0;
+  while (done < count) {
+    size_t left = count - done;
+    size_t bytes_left = left * wsz;
+    int al = algo;
+    if (al == B200C_ALGO_AUTO) {
+      if (bytes_left <= c->cfg.oneshot_max_bytes) al = B200C_ALGO_ONESHOT;
+      else if (nvls_ok && W > 2 && bytes_left >= c->cfg.nvls_min_bytes) al = B200C_ALGO_NVLS;
+      else al = B200C_ALGO_TWOSHOT;
+    }
+    CollArgs a;
+    base_args(c, &a);
+    a.in = in + done * esz; a.out = out + done * esz;
+    a.has_scale = has_scale; a.scale = scale;
+    size_t n;
+    int grid;
+    // symmetric zero-copy NVLS: buffer lives in the symmetric region at the same offset everywhere
+    bool sym = false;
+    if (al == B200C_ALGO_NVLS && wire == dtype && send == recv && c->sym_bytes) {
+      char* base = c->arena[c->rank] + c->off_sym;
+      if (in >= base && in + count * esz <= base + c->sym_bytes && (((uintptr_t)a.in) & 15) == 0 && (left * esz) % 16 == 0) sym = true;
+    }
+    if (al == B200C_ALGO_ONESHOT) {
+      size_t cap = c->cfg.staging_bytes / W / wsz / vec * vec;  // elements per slot
+      n = left < cap ? left : cap;
+      a.chunk = round_up(n, vec);
+      plan_tiles(n, wsz, vec, c->cfg.max_blocks, kMinTileBytes, &a.tile, &grid);
+    } else if (al == B200C_ALGO_TWOSHOT) {
+      size_t cap_chunk = c->cfg.staging_bytes / W / wsz / vec * vec;
+      size_t cap = cap_chunk * W;
+      n = left < cap ? left : cap;
+      a.chunk = round_up((n + W - 1) / W, vec);
+      plan_tiles(a.chunk, wsz, vec, c->cfg.max_blocks, kMinTileBytes, &a.tile, &grid);
+    } else {
+      size_t cap = sym ? left : c->cfg.staging_bytes / wsz / vec * vec;
+      n = left < cap ? left : cap;
+      a.chunk = round_up((n + W - 1) / W, vec);
+      a.symmetric = sym ? 1 : 0;
+      a.sym_off = sym ? (size_t)((const char*)a.in - c->arena[c->rank]) : 0;
+      plan_tiles(a.chunk, wsz, vec, c->cfg.max_blocks, kMinTileBytes, &a.tile, &grid);
+    }
+    a.n = n;
+    a.sig = make_sig(OPC_ALLREDUCE, dtype * 16 + wire, op, n, -1, al * 2 + (sym ? 1 : 0));
+    if (al == B200C_ALGO_NVLS) {
+      if (dtype == B200C_FLOAT32 && wire == B200C_FLOAT32) launch_nvls<float, float>(a, grid, s);
+      else if (dtype == B200C_BFLOAT16) launch_nvls<bf16_t, bf16_t>(a, grid, s);
+      else if (dtype == B200C_FLOAT16) launch_nvls<f16_t, f16_t>(a, grid, s);
+      else if (wire == B200C_BFLOAT16) launch_nvls<float, bf16_t>(a, grid, s);
+      else launch_nvls<float, f16_t>(a, grid, s);
+    } else if (wire != dtype) {
+      if (wire == B200C_BFLOAT16) launch_mixed<float, bf16_t>(al, a, grid, s);
+      else launch_mixed<float, f16_t>(al, a, grid, s);
+    } else {
+      rc = launch_same_type(dtype, al == B200C_ALGO_ONESHOT ? KIND_ONESHOT : KIND_TWOSHOT, op, a, grid, s);
+      if (rc) return rc;
+    }
+    rc = launch_check("allreduce");
+    if (rc) return rc;
+    done += n;
+  }
+  return B200C_OK;
+}
+
+extern "C" int b200c_allreduce(b200c_comm_t* c, const void* send, void* recv, size_t count, int dtype, int op, int algo,
+                               b200c_stream_t stream) {
+  // AVG on integers: SUM then truncating divide by world (ncclAvg semantics); handled by apply_scale.
+  return allreduce_impl(c, send, recv, count, dtype, dtype, op, 1.f, 0, algo, (cudaStream_t)stream);
+}
+
+extern "C" int b200c_allreduce_scaled(b200c_comm_t* c, const void* send, void* recv, size_t count, int dtype, int wire_dtype,
+                                      float scale, int algo, b200c_stream_t stream) {
+  if (dtype != B200C_FLOAT32 && dtype != B200C_BFLOAT16 && dtype != B200C_FLOAT16)
+    return fail(B200C_EUNSUPPORTED, "scaled allreduce supports f32/bf16/f16 buffers, got %d", dtype);
+  return allreduce_impl(c, send, recv, count, dtype, wire_dtype, B200C_SUM, scale, 1, algo, (cudaStream_t)stream);
+}
+
+extern "C" int b200c_reduce(b200c_comm_t* c, const void* send, void* recv, size_t count, int dtype, int op, int root,
+                            b200c_stream_t stream) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  size_t esz = b200c_dtype_size(dtype);
+  if (!esz) return fail(B200C_EINVAL, "bad dtype %d", dtype);
+  if (op < 0 || op >= B200C_NUM_OPS) return fail(B200C_EINVAL, "bad reduce op %d", op);
+  if (root < 0 || root >= c->world) return fail(B200C_EINVAL, "bad root %d", root);
+  if (count == 0) return B200C_OK;
+  if (!send || (c->rank == root && !recv)) return fail(B200C_EINVAL, "null buffer");
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceGuard g(c->device);
+  if (c->world == 1) {
+    if (send != recv) RT(cudaMemcpyAsync(recv, send, count * esz, cudaMemcpyDeviceToDevice, s));
+    return B200C_OK;
+  }
+  const size_t vec = 16 / esz;
+  size_t cap = c->cfg.staging_bytes / c->world / esz / vec * vec;
+  size_t done = 0;
+  while (done < count) {
+    size_t n = count - done < cap ? count - done : cap;
+    CollArgs a;
+    base_args(c, &a);
+    a.in = static_cast<const char*>(send) + done * esz;
+    a.out = recv ? static_cast<char*>(recv) + done * esz : nullptr;
+    a.n = n; a.chunk = round_up(n, vec); a.root = root;
+    if (op == B200C_AVG) { a.has_scale = 1; a.scale = 1.f / c->world; }
+    int grid;
+    plan_tiles(n, esz, vec, c->cfg.max_blocks, kMinTileBytes, &a.tile, &grid);
+    a.sig = make_sig(OPC_REDUCE, dtype, op, n, root, 0);
+    rc = launch_same_type(dtype, KIND_REDUCE, op, a, grid, s);
+    if (rc) return rc;
+    rc = launch_check("reduce");
+    if (rc) return rc;
+    done += n;
+  }
+  return B200C_OK;
+}
+
+extern "C" int b200c_reducescatter(b200c_comm_t* c, const void* const* send_ptrs, void* recv, size_t count, int dtype, int op,
+                                   b200c_stream_t stream) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  size_t esz = b200c_dtype_size(dtype);
+  if (!esz) return fail(B200C_EINVAL, "bad dtype %d", dtype);
+  if (op < 0 || op >= B200C_NUM_OPS) return fail(B200C_EINVAL, "bad reduce op %d", op);
+  if (count == 0) return B200C_OK;
+  if (!send_ptrs || !recv) return fail(B200C_EINVAL, "null buffer");
+  for (int j = 0; j < c->world; j++) if (!send_ptrs[j]) return fail(B200C_EINVAL, "send_ptrs[%d] is null", j);
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceGuard g(c->device);
+  if (c->world == 1) {
+    if (send_ptrs[0] != recv) RT(cudaMemcpyAsync(recv, send_ptrs[0], count * esz, cudaMemcpyDeviceToDevice, s));
+    return B200C_OK;
+  }
+  const size_t vec = 16 / esz;
+  size_t cap = c->cfg.staging_bytes / c->world / esz / vec * vec;
+  size_t done = 0;
+  while (done < count) {
+    size_t n = count - done < cap ? count - done : cap;
+    CollArgs a;
+    base_args(c, &a);
+    for (int j = 0; j < c->world; j++) a.in_ptrs[j] = static_cast<const char*>(send_ptrs[j]) + done * esz;
+    a.out = static_cast<char*>(recv) + done * esz;
+    a.n = n; a.chunk = round_up(n, vec);
+    if (op == B200C_AVG) { a.has_scale = 1; a.scale = 1.f / c->world; }
+    int grid;
+    plan_tiles(n, esz, vec, c->cfg.max_blocks, kMinTileBytes, &a.tile, &grid);
+    a.sig = make_sig(OPC_REDUCESCATTER, dtype, op, n, -1, 0);
+    rc = launch_same_type(dtype, KIND_REDUCESCATTER, op, a, grid, s);
+    if (rc) return rc;
+    rc = launch_check("reducescatter");
+    if (rc) return rc;
+    done += n;
+  }
+  return B200C_OK;
+}
+
+extern "C" int b200c_allgather(b200c_comm_t* c, const void* send, void* const* recv_ptrs, size_t count, int dtype,
+                               b200c_stream_t stream) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  size_t esz = b200c_dtype_size(dtype);
+  if (!esz) return fail(B200C_EINVAL, "bad dtype %d", dtype);
+  if (count == 0) return B200C_OK;
+  if (!send || !recv_ptrs) return fail(B200C_EINVAL, "null buffer");
+  for (int j = 0; j < c->world; j++) if (!recv_ptrs[j]) return fail(B200C_EINVAL, "recv_ptrs[%d] is null", j);
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceGuard g(c->device);
+  size_t bytes = count * esz;
+  if (c->world == 1) {
+    if (send != recv_ptrs[0]) RT(cudaMemcpyAsync(recv_ptrs[0], send, bytes, cudaMemcpyDeviceToDevice, s));
+    return B200C_OK;
+  }
+  size_t cap = c->cfg.staging_bytes / c->world / 16 * 16;
+  size_t done = 0;
+  while (done < bytes) {
+    size_t n = bytes - done < cap ? bytes - done : cap;
+    CollArgs a;
+    base_args(c, &a);
+    a.in = static_cast<const char*>(send) + done;
+    for (int j = 0; j < c->world; j++) a.out_ptrs[j] = static_cast<char*>(recv_ptrs[j]) + done;
+    a.n = n; a.chunk = round_up(n, 16);
+    int grid;
+    plan_tiles(n, 1, 16, c->cfg.max_blocks, kMinTileBytes, &a.tile, &grid);
+    a.sig = make_sig(OPC_ALLGATHER, dtype, 0, n, -1, 0);
+    k_allgather<<<grid, kThreads, 0, s>>>(a);
+    rc = launch_check("allgather");
+    if (rc) return rc;
+    done += n;
+  }
+  return B200C_OK;
+}
+
+extern "C" int b200c_broadcast(b200c_comm_t* c, void* buf, size_t count, int dtype, int root, b200c_stream_t stream) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  size_t esz = b200c_dtype_size(dtype);
+  if (!esz) return fail(B200C_EINVAL, "bad dtype %d", dtype);
+  if (root < 0 || root >= c->world) return fail(B200C_EINVAL, "bad root %d", root);
+  if (count == 0 || c->world == 1) return B200C_OK;
+  if (!buf) return fail(B200C_EINVAL, "null buffer");
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceGuard g(c->device);
+  size_t bytes = count * esz, cap = c->cfg.staging_bytes / 16 * 16, done = 0;
+  while (done < bytes) {
+    size_t n = bytes - done < cap ? bytes - done : cap;
+    CollArgs a;
+    base_args(c, &a);
+    a.in = static_cast<char*>(buf) + done; a.out = static_cast<char*>(buf) + done;
+    a.n = n; a.chunk = round_up(n, 16); a.root = root;
+    int grid;
+    plan_tiles(n, 1, 16, c->cfg.max_blocks, kMinTileBytes, &a.tile, &grid);
+    a.sig = make_sig(OPC_BROADCAST, dtype, 0, n, root, 0);
+    k_broadcast<<<grid, kThreads, 0, s>>>(a);
+    rc = launch_check("broadcast");
+    if (rc) return rc;
+    done += n;
+  }
+  return B200C_OK;
+}
+
+extern "C" int b200c_barrier(b200c_comm_t* c, b200c_stream_t stream) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (c->world == 1) return B200C_OK;
+  DeviceGuard g(c->device);
+  CollArgs a;
+  base_args(c, &a);
+  a.sig = make_sig(OPC_BARRIER, 0, 0, 0, -1, 0);
+  k_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+  return launch_check("barrier");
+}
+
+static int p2p_impl(b200c_comm* c, void* buf, size_t bytes, int peer, bool is_send, cudaStream_t s) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (peer < 0 || peer >= c->world) return fail(B200C_EINVAL, "bad peer %d", peer);
+  if (peer == c->rank) return fail(B200C_EINVAL, "send/recv to self (rank %d)", peer);
+  if (bytes == 0) return B200C_OK;
+  if (!buf) return fail(B200C_EINVAL, "null buffer");
+  DeviceGuard g(c->device);
+  P2PArgs a;
+  memset(&a, 0, sizeof a);
+  a.c = c->dev; a.buf = buf; a.bytes = bytes; a.peer = peer;
+  size_t cb = c->cfg.p2p_slot_bytes;
+  size_t ncells = (bytes + cb - 1) / cb;
+  if (ncells > 0x7fffffffull) return fail(B200C_EINVAL, "message too large for the cell ring");
+  uint32_t* ctr = is_send ? &c->send_cells[peer] : &c->recv_cells[peer];
+  a.first_cell = *ctr; a.ncells = (uint32_t)ncells;
+  *ctr += (uint32_t)ncells;
+  // no block may wait on a cell that one of its own later iterations has to free: grid <= ring size
+  uint32_t grid = (uint32_t)ncells;
+  uint32_t lim = c->cfg.max_blocks < c->cfg.p2p_slots ? c->cfg.max_blocks : c->cfg.p2p_slots;
+  if (grid > lim) grid = lim;
+  if (is_send) k_send<<<grid, kThreads, 0, s>>>(a);
+  else k_recv<<<grid, kThreads, 0, s>>>(a);
+  return launch_check(is_send ? "send" : "recv");
+}
+extern "C" int b200c_send(b200c_comm_t* c, const void* buf, size_t bytes, int peer, b200c_stream_t stream) {
+  return p2p_impl(c, const_cast<void*>(buf), bytes, peer, true, (cudaStream_t)stream);
+}
+extern "C" int b200c_recv(b200c_comm_t* c, void* buf, size_t bytes, int peer, b200c_stream_t stream) {
+  return p2p_impl(c, buf, bytes, peer, false, (cudaStream_t)stream);
+}

@@ -1,0 +1,127 @@
+// Untyped (byte-moving) kernels: allgather, broadcast, barrier, p2p send/recv.
+// Included by exactly one translation unit (b200coll.cu).
+#pragma once
+#include "coll_kernels.cuh"
+
+namespace b200c {
+
+// ---------------------------------------------------------------------------------------------
+// allgather: push own tensor to slot [r] of every peer, then copy the W slots into the caller's
+// W output tensors (out_ptrs[j]).  Pure byte movement -> instantiated once (uint8_t).
+// broadcast: root pushes into slot 0 of every peer; peers copy out.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_allgather(CollArgs a) {
+  const DevComm& c = a.c;
+  const int r = c.rank, W = c.world;
+  if (!coll_prologue(a)) return;
+  const size_t t0 = (size_t)blockIdx.x * a.tile;           // bytes
+  const size_t cnt = clip_count(t0, t0 + a.tile, a.n);     // n = bytes per rank
+  const size_t slot_bytes = a.chunk;
+  const uint8_t* in = static_cast<const uint8_t*>(a.in);
+  if (cnt) {
+    for (int k = 1; k < W; k++) {
+      int j = r + k; if (j >= W) j -= W;
+      copy_tile<uint8_t, false>(staging_ptr<uint8_t>(c, j, a.seq, (size_t)r * slot_bytes) + t0, in + t0, cnt);
+    }
+    uint8_t* own_out = static_cast<uint8_t*>(a.out_ptrs[r]);
+    if (own_out + t0 != in + t0) copy_tile<uint8_t, false>(own_out + t0, in + t0, cnt);
+  }
+  block_signal_all(kOffFlagA, a.seq, c);
+  if (!block_wait_all(my_flags(kOffFlagA, c), a.seq, c, 1)) return;
+  check_signature(a);
+  if (cnt) {
+    for (int k = 1; k < W; k++) {
+      int j = r + k; if (j >= W) j -= W;
+      copy_tile<uint8_t, true>(static_cast<uint8_t*>(a.out_ptrs[j]) + t0, staging_ptr<uint8_t>(c, r, a.seq, (size_t)j * slot_bytes) + t0, cnt);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_broadcast(CollArgs a) {
+  const DevComm& c = a.c;
+  const int r = c.rank, W = c.world, root = a.root;
+  if (!coll_prologue(a)) return;
+  const size_t t0 = (size_t)blockIdx.x * a.tile;           // bytes
+  const size_t cnt = clip_count(t0, t0 + a.tile, a.n);
+  if (r == root) {
+    if (cnt) {
+      for (int k = 1; k < W; k++) {
+        int j = r + k; if (j >= W) j -= W;
+        copy_tile<uint8_t, false>(staging_ptr<uint8_t>(c, j, a.seq, 0) + t0, static_cast<const uint8_t*>(a.in) + t0, cnt);
+      }
+    }
+    block_signal_all(kOffFlagA, a.seq, c);
+  } else {
+    if (!block_wait_one(my_flags(kOffFlagA, c) + root, a.seq, c, root, 1)) return;
+    check_signature(a);
+    if (cnt) copy_tile<uint8_t, true>(static_cast<uint8_t*>(a.out) + t0, staging_ptr<uint8_t>(c, r, a.seq, 0) + t0, cnt);
+  }
+}
+
+// barrier: arrive[] exchange only (the prologue publishes arrive = seq; wait for everyone at seq).
+__global__ void __launch_bounds__(32) k_barrier(CollArgs a) {
+  const DevComm& c = a.c;
+  int t = threadIdx.x;
+  if (t < c.world && t != c.rank) {
+    st_release_sys(reinterpret_cast<uint32_t*>(c.arena[t] + kOffArrive) + c.rank, a.seq);
+    wait_flag(reinterpret_cast<const uint32_t*>(c.arena[c.rank] + kOffArrive) + t, a.seq, c, t, 0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// p2p: ring of cells in the receiver's arena, one ready flag and one ack flag per cell.
+// Cell k of the pair's lifetime lives at ring position k % cells and carries flag value k+1.
+// ---------------------------------------------------------------------------------------------
+struct P2PArgs {
+  DevComm c;
+  void* buf;          // user buffer (send: source, recv: destination)
+  size_t bytes;
+  int peer;
+  uint32_t first_cell;  // cumulative cell index of this message's first cell
+  uint32_t ncells;
+};
+
+__global__ void __launch_bounds__(kThreads) k_send(P2PArgs a) {
+  const DevComm& c = a.c;
+  const int r = c.rank, d = a.peer;
+  const size_t cb = c.p2p_cell_bytes;
+  const uint8_t* src = static_cast<const uint8_t*>(a.buf);
+  for (uint32_t i = blockIdx.x; i < a.ncells; i += gridDim.x) {
+    uint32_t k = a.first_cell + i;
+    uint32_t pos = k % (uint32_t)c.p2p_cells;
+    // the previous occupant of this ring position (cell k - cells) must have been consumed
+    if (k >= (uint32_t)c.p2p_cells) {
+      const uint32_t* ack = reinterpret_cast<const uint32_t*>(c.arena[r] + kOffP2PAck) + (size_t)d * kMaxCells + pos;
+      if (!block_wait_one(ack, k + 1 - (uint32_t)c.p2p_cells, c, d, 4)) return;
+    }
+    size_t off = (size_t)i * cb;
+    size_t cnt = a.bytes - off < cb ? a.bytes - off : cb;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(c.arena[d] + c.off_p2p + ((size_t)r * c.p2p_cells + pos) * cb);
+    copy_tile<uint8_t, false>(dst, src + off, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0)
+      st_release_sys(reinterpret_cast<uint32_t*>(c.arena[d] + kOffP2PReady) + (size_t)r * kMaxCells + pos, k + 1);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_recv(P2PArgs a) {
+  const DevComm& c = a.c;
+  const int r = c.rank, s = a.peer;
+  const size_t cb = c.p2p_cell_bytes;
+  uint8_t* dstbuf = static_cast<uint8_t*>(a.buf);
+  for (uint32_t i = blockIdx.x; i < a.ncells; i += gridDim.x) {
+    uint32_t k = a.first_cell + i;
+    uint32_t pos = k % (uint32_t)c.p2p_cells;
+    const uint32_t* ready = reinterpret_cast<const uint32_t*>(c.arena[r] + kOffP2PReady) + (size_t)s * kMaxCells + pos;
+    if (!block_wait_one(ready, k + 1, c, s, 3)) return;
+    size_t off = (size_t)i * cb;
+    size_t cnt = a.bytes - off < cb ? a.bytes - off : cb;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(c.arena[r] + c.off_p2p + ((size_t)s * c.p2p_cells + pos) * cb);
+    copy_tile<uint8_t, true>(dstbuf + off, src, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0)
+      st_release_sys(reinterpret_cast<uint32_t*>(c.arena[s] + kOffP2PAck) + (size_t)r * kMaxCells + pos, k + 1);
+  }
+}
+
+}  // namespace b200c

@@ -1,0 +1,5 @@
+// Instantiates the same-type collective kernels for uint64_t.
+#include "launch_typed.cuh"
+namespace b200c {
+int launch_u64(int kind, int op, const CollArgs& a, int grid, cudaStream_t s) { return launch_typed_impl<uint64_t>(kind, op, a, grid, s); }
+}  // namespace b200c
