@@ -206,6 +206,28 @@ class PeerMemoryComm:
             if self.rank == 0:
                 rendezvous.cleanup_keys(self.store, self.key, self.world_size)
 
+    def symmetric_tensor(self, shape, dtype, byte_offset: int = 0):
+        """A torch tensor aliasing this rank's symmetric region at `byte_offset`.  The same offset
+        names the same logical buffer on every rank; collectives on such a tensor run zero-copy
+        (NVLS reduces and broadcasts it in place)."""
+        import torch
+
+        base = self.lib.b200c_comm_symmetric_base(self._h())
+        total = int(self.lib.b200c_comm_symmetric_bytes(self._h()))
+        numel = 1
+        for d in (shape if isinstance(shape, (tuple, list)) else (shape,)):
+            numel *= int(d)
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        if not base or byte_offset % 16 or byte_offset + nbytes > total:
+            raise RuntimeError(f"symmetric region too small or offset unaligned: need {byte_offset}+{nbytes} of {total} bytes "
+                               "(set B200COLL_SYMMETRIC_MB / config.symmetric_bytes)")
+
+        class _Holder:
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (base + byte_offset, False), "version": 2}
+
+        raw = torch.as_tensor(_Holder(), device=torch.device("cuda", self.device))
+        return raw.view(dtype).view(shape)
+
     def _h(self):
         if self.handle is None:
             raise RuntimeError("B200 communicator has been destroyed.")

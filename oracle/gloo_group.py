@@ -50,7 +50,11 @@ class GlooGroup:
         timeout_s = (gloo_timeout or 30000) / 1000.0
         if not dist.is_initialized():
             store = store if store is not None else rendezvous.default_store()
-            key = f"collective_group_master_address_{group_name}"
+            # the n-th incarnation of a group name gets its own key, otherwise a re-created group could
+            # read the previous incarnation's (dead) address
+            from ant_ray_b200.b200_group import next_comm_key
+
+            key = "collective_group_master_address_" + next_comm_key(group_name)
             if rank == 0:
                 store.set(key, f"127.0.0.1:{_free_port()}".encode())
             addr, port = store.get(key, timeout_s).decode().split(":")

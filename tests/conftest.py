@@ -4,6 +4,9 @@ import sys
 
 import pytest
 
+# W loopback ranks need W concurrently running streams; the default is 8 hardware queues
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

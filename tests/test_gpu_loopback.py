@@ -1,0 +1,246 @@
+"""GPU parity tests that need ONE GPU: W communicators in one process (ant_ray_b200.loopback).
+
+Every op goes through the C-ABI (ctypes -> libb200coll.so) and is compared with the CPU oracle on
+the same seeded inputs: bit-exact for every dtype, floats included, because the peer-memory kernels
+fold ranks in the oracle's order (0..W-1, fp32 accumulate for f16/bf16).
+Sizes cover empty, tiny, ragged (not a multiple of the 16-byte vector or of W), multi-block and
+multi-piece (larger than the staging half) messages.
+"""
+import pytest
+import torch
+
+from gpu_common import FLOAT_DTYPES, INT_DTYPES, NATIVE, assert_equal_bits, make_input
+
+from ant_ray_b200 import _native as N
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+OPS = {"sum": (N.SUM, O.SUM), "prod": (N.PROD, O.PROD), "max": (N.MAX, O.MAX), "min": (N.MIN, O.MIN), "avg": (N.AVG, O.AVG)}
+SIZES = [1, 3, 10, 257, 4096 + 5, 100_003]
+
+
+@pytest.fixture(scope="module", params=[2, 4, 8])
+def world(request):
+    from ant_ray_b200.loopback import LoopbackWorld
+
+    w = LoopbackWorld(request.param, device=0, key=f"lb{request.param}", staging_bytes=1 << 20, timeout_ms=20000)
+    yield w
+    w.destroy()
+
+
+def _run_allreduce(world, dtype, n, opname, algo, inplace=True):
+    W = world.world_size
+    nat, orc = OPS[opname]
+    ins = [make_input(dtype, n, r, opname) for r in range(W)]
+    dev_in = [t.cuda() for t in ins]
+    dev_out = dev_in if inplace else [torch.empty_like(t) for t in dev_in]
+    world.run(lambda r, c: c.allreduce(dev_in[r].data_ptr(), dev_out[r].data_ptr(), n, NATIVE[dtype], nat, algo))
+    torch.cuda.synchronize()
+    world.check()
+    want = O.allreduce(ins, orc)
+    for r in range(W):
+        assert_equal_bits(dev_out[r], want, f"allreduce {dtype} n={n} op={opname} algo={algo} rank={r}")
+        if not inplace:
+            assert_equal_bits(dev_in[r], ins[r], "input must be untouched")
+
+
+@pytest.mark.parametrize("algo", [N.ALGO_ONESHOT, N.ALGO_TWOSHOT])
+@pytest.mark.parametrize("dtype", INT_DTYPES + FLOAT_DTYPES)
+def test_allreduce_sum_all_dtypes(world, dtype, algo):
+    for n in SIZES:
+        _run_allreduce(world, dtype, n, "sum", algo)
+
+
+@pytest.mark.parametrize("algo", [N.ALGO_ONESHOT, N.ALGO_TWOSHOT])
+@pytest.mark.parametrize("opname", ["prod", "max", "min", "avg"])
+@pytest.mark.parametrize("dtype", [torch.int32, torch.int64, torch.uint8, torch.float32, torch.bfloat16, torch.float16, torch.float64])
+def test_allreduce_ops(world, dtype, opname, algo):
+    for n in (7, 5000):
+        _run_allreduce(world, dtype, n, opname, algo)
+
+
+def test_allreduce_out_of_place_and_auto(world):
+    for n in (5, 70_000):
+        _run_allreduce(world, torch.float32, n, "sum", N.ALGO_AUTO, inplace=False)
+
+
+def test_allreduce_multi_piece(world):
+    # staging half is 1 MiB here: 3 MiB of fp32 needs several pieces under every algorithm
+    for algo in (N.ALGO_ONESHOT, N.ALGO_TWOSHOT, N.ALGO_AUTO):
+        _run_allreduce(world, torch.float32, 3 * (1 << 18) + 11, "sum", algo)
+
+
+def test_allreduce_unaligned_views(world):
+    """Tensor views that start 4 bytes into an allocation take the scalar path."""
+    W, n = world.world_size, 1001
+    ins = [make_input(torch.float32, n + 1, r) for r in range(W)]
+    dev = [t.cuda() for t in ins]
+    for algo in (N.ALGO_ONESHOT, N.ALGO_TWOSHOT):
+        cur = [d.clone() for d in dev]
+        world.run(lambda r, c: c.allreduce(cur[r][1:].data_ptr(), cur[r][1:].data_ptr(), n, N.FLOAT32, N.SUM, algo))
+        torch.cuda.synchronize()
+        want = O.allreduce([t[1:] for t in ins])
+        for r in range(W):
+            assert_equal_bits(cur[r][1:], want, f"unaligned algo={algo}")
+            assert cur[r][0].item() == ins[r][0].item()
+
+
+def test_allreduce_empty(world):
+    x = [torch.empty(0, device="cuda") for _ in range(world.world_size)]
+    world.run(lambda r, c: c.allreduce(x[r].data_ptr(), x[r].data_ptr(), 0, N.FLOAT32, N.SUM))
+    torch.cuda.synchronize()
+    world.check()
+
+
+@pytest.mark.parametrize("wire", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("algo", [N.ALGO_ONESHOT, N.ALGO_TWOSHOT])
+def test_fused_gradient_mean(world, wire, algo):
+    """K13: fp32 bucket, 16-bit wire, fp32 accumulate, x 1/W, all in one launch."""
+    W = world.world_size
+    for n in (9, 33_333):
+        ins = [make_input(torch.float32, n, r) for r in range(W)]
+        dev = [t.cuda() for t in ins]
+        world.run(lambda r, c: c.allreduce_scaled(dev[r].data_ptr(), dev[r].data_ptr(), n, N.FLOAT32, NATIVE[wire], 1.0 / W, algo))
+        torch.cuda.synchronize()
+        world.check()
+        want = O.allreduce_scaled(ins, None if wire == torch.float32 else wire, 1.0 / W)
+        for r in range(W):
+            assert_equal_bits(dev[r], want, f"fused mean wire={wire} n={n} rank={r}")
+        # sanity against plain fp32 math: the mean, to the wire's precision
+        ref = torch.stack(ins).mean(0)
+        tol = {torch.float32: 1e-5, torch.bfloat16: 2e-2, torch.float16: 2e-3}[wire]
+        assert torch.allclose(dev[0].cpu(), ref, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.int32, torch.float32, torch.bfloat16, torch.uint8])
+def test_reducescatter(world, dtype):
+    W = world.world_size
+    for n in (6, 20_001):
+        lists = [[make_input(dtype, n, r * 16 + j) for j in range(W)] for r in range(W)]
+        dev = [[t.cuda() for t in row] for row in lists]
+        outs = [torch.empty(n, dtype=dtype, device="cuda") for _ in range(W)]
+        world.run(lambda r, c: c.reducescatter([t.data_ptr() for t in dev[r]], outs[r].data_ptr(), n, NATIVE[dtype], N.SUM))
+        torch.cuda.synchronize()
+        world.check()
+        want = O.reducescatter(lists)
+        for r in range(W):
+            assert_equal_bits(outs[r], want[r], f"reducescatter {dtype} n={n} rank={r}")
+            for j in range(W):
+                assert_equal_bits(dev[r][j], lists[r][j], "inputs must be untouched")
+
+
+@pytest.mark.parametrize("dtype", [torch.int64, torch.float16, torch.uint8])
+def test_allgather(world, dtype):
+    W = world.world_size
+    for n in (1, 13, 50_001):
+        ins = [make_input(dtype, n, r) for r in range(W)]
+        dev = [t.cuda() for t in ins]
+        outs = [[torch.zeros(n, dtype=dtype, device="cuda") for _ in range(W)] for _ in range(W)]
+        world.run(lambda r, c: c.allgather(dev[r].data_ptr(), [t.data_ptr() for t in outs[r]], n, NATIVE[dtype]))
+        torch.cuda.synchronize()
+        world.check()
+        for r in range(W):
+            for j in range(W):
+                assert_equal_bits(outs[r][j], ins[j], f"allgather {dtype} n={n} rank={r} slot={j}")
+
+
+def test_broadcast_and_reduce(world):
+    W = world.world_size
+    for root in (0, W - 1):
+        for n in (3, 40_000):
+            ins = [make_input(torch.float32, n, r) for r in range(W)]
+            dev = [t.cuda() for t in ins]
+            world.run(lambda r, c: c.broadcast(dev[r].data_ptr(), n, N.FLOAT32, root))
+            torch.cuda.synchronize()
+            for r in range(W):
+                assert_equal_bits(dev[r], ins[root], f"broadcast root={root} rank={r}")
+            dev = [t.cuda() for t in ins]
+            world.run(lambda r, c: c.reduce(dev[r].data_ptr(), dev[r].data_ptr(), n, N.FLOAT32, N.SUM, root))
+            torch.cuda.synchronize()
+            world.check()
+            want = O.reduce(ins)
+            for r in range(W):
+                assert_equal_bits(dev[r], want if r == root else ins[r], f"reduce root={root} rank={r}")
+
+
+def test_send_recv(world):
+    W = world.world_size
+    for nbytes in (1, 100_000, (32 << 10) * 300 + 17):  # the last one wraps the 256-cell ring
+        src = torch.randint(0, 255, (nbytes,), dtype=torch.uint8, generator=torch.Generator().manual_seed(7))
+        d_src = src.cuda()
+        d_dst = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+
+        def step(r, c):
+            if r == 0:
+                c.send(d_src.data_ptr(), nbytes, 1)
+            elif r == 1:
+                c.recv(d_dst.data_ptr(), nbytes, 0)
+
+        world.run(step)
+        torch.cuda.synchronize()
+        world.check()
+        assert_equal_bits(d_dst, src, f"send/recv {nbytes} bytes")
+
+
+def test_barrier_and_back_to_back(world):
+    """200 small collectives in a row exercise the double-buffered staging and the flag epochs."""
+    W, n = world.world_size, 300
+    ins = [make_input(torch.int32, n, r) for r in range(W)]
+    dev = [t.cuda() for t in ins]
+    acc = [t.clone() for t in ins]
+    for it in range(200):
+        world.run(lambda r, c: c.allreduce(dev[r].data_ptr(), dev[r].data_ptr(), n, N.INT32, N.SUM, N.ALGO_ONESHOT if it % 2 else N.ALGO_TWOSHOT))
+        s = O.allreduce(acc)
+        acc = [s.clone() for _ in range(W)]
+        if it % 50 == 0:
+            world.run(lambda r, c: c.barrier())
+    torch.cuda.synchronize()
+    world.check()
+    for r in range(W):
+        assert_equal_bits(dev[r], acc[r], "after 200 allreduces")
+
+
+def test_mismatch_is_detected_not_hung():
+    """Ranks that disagree on the element count must surface an error instead of hanging or reading
+    out of bounds (reference expectation: test_torch_tensor_dag.py:1544-1588)."""
+    from ant_ray_b200.loopback import LoopbackWorld
+
+    w = LoopbackWorld(2, device=0, key="lb-mismatch", staging_bytes=1 << 20, timeout_ms=3000)
+    try:
+        x = [torch.ones(64, device="cuda"), torch.ones(128, device="cuda")]
+        w.run(lambda r, c: c.allreduce(x[r].data_ptr(), x[r].data_ptr(), x[r].numel(), N.FLOAT32, N.SUM, N.ALGO_ONESHOT))
+        torch.cuda.synchronize()
+        with pytest.raises(N.B200CollError) as ei:
+            w.check()
+        assert ei.value.status in (N.EMISMATCH, N.ETIMEOUT, N.EABORTED)
+        with pytest.raises(RuntimeError):  # the communicator stays poisoned
+            w.comms[0].allreduce(x[0].data_ptr(), x[0].data_ptr(), 64, N.FLOAT32, N.SUM)
+    finally:
+        w.destroy()
+
+
+def test_abort_unblocks_a_waiting_kernel():
+    """destroy()/abort must release a kernel that waits for a peer that never comes
+    (reference: _NcclGroup.destroy -> comm.abort(), nccl_group.py:347-365)."""
+    import time
+
+    from ant_ray_b200.loopback import LoopbackWorld
+
+    w = LoopbackWorld(2, device=0, key="lb-abort", staging_bytes=1 << 20, timeout_ms=60000)
+    try:
+        x = torch.ones(64, device="cuda")
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            w.comms[0].allreduce(x.data_ptr(), x.data_ptr(), 64, N.FLOAT32, N.SUM)  # rank 1 never joins
+        time.sleep(0.2)
+        assert not s.query()
+        t0 = time.time()
+        w.comms[0].abort()
+        s.synchronize()
+        assert time.time() - t0 < 5
+        with pytest.raises(N.B200CollError) as ei:
+            w.comms[0].check()
+        assert ei.value.status == N.EABORTED
+    finally:
+        w.destroy()
