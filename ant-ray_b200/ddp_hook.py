@@ -14,6 +14,7 @@ Attachment point: `DistributedDataParallel.register_comm_hook(state, hook)` with
 mean.  The kernel is enqueued on a dedicated communication stream so it overlaps the rest of the
 backward pass, like the NCCL stream of the default reducer.
 """
+import os
 from typing import Optional
 
 import torch
@@ -83,6 +84,12 @@ def make_grad_state(world_size: Optional[int] = None, rank: Optional[int] = None
         world_size = dist.get_world_size() if dist.is_initialized() else 1
     if rank is None:
         rank = dist.get_rank() if dist.is_initialized() else 0
+    if config is None:
+        # The reduction runs beside the backward pass: a small grid leaves the SMs to the convolutions
+        # (the bucket traffic needs a tiny fraction of NVLink), like NCCL's handful of channels.
+        from .b200_group import make_config
+
+        config = make_config(max_blocks=int(os.environ.get("B200COLL_HOOK_MAX_BLOCKS", "32")))
     comm = PeerMemoryComm(world_size, rank, next_comm_key("train/" + name), device, store, config)
     return B200GradState(comm, wire=wire, **kw)
 

@@ -35,6 +35,11 @@ NVLINK_PEAK_MEASURED = 770.0   # GB/s per direction per GPU, peer copy (B200_PRO
 NVLINK_PEAK_NOMINAL = 900.0
 
 
+def log(msg):
+    if int(os.environ.get("RANK", 0)) == 0:
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -261,7 +266,15 @@ def run_sweep_loopback(max_bytes):
 # ------------------------------------------------------------------------------------------------
 # reference CPU path: torch DDP over gloo on the host cores (bounded sample)
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker(rank, world, port, batch, steps, warmup, threads, q):
+def cpu_has_bf16():
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        return False
+    return "avx512_bf16" in flags or "amx_bf16" in flags
+
+
+def _cpu_worker(rank, world, port, batch, steps, warmup, threads, q, use_bf16, budget_s):
     import torch
     import torch.distributed as dist
     from torch.nn.parallel import DistributedDataParallel
@@ -272,24 +285,34 @@ def _cpu_worker(rank, world, port, batch, steps, warmup, threads, q):
     device = torch.device("cpu")
     model = DistributedDataParallel(build_model(device, channels_last=False))
     opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9)
-    step = make_step(model, opt, use_autocast=True, device=device)
+    step = make_step(model, opt, use_autocast=use_bf16, device=device)
     g = torch.Generator().manual_seed(rank)
     x = torch.randn(batch, 3, 224, 224, generator=g)
     y = torch.randint(0, 1000, (batch,), generator=g)
+    t_begin = time.time()
     for _ in range(warmup):
         step(x, y)
+        if time.time() - t_begin > budget_s / 2:
+            break
     dist.barrier()
     t0 = time.time()
+    done = 0
+    stop = torch.zeros(1)
     for _ in range(steps):
         step(x, y)
-    dist.barrier()
+        done += 1
+        # bounded sample: every rank stops together once the time budget is spent
+        stop[0] = 1.0 if time.time() - t_begin > budget_s else 0.0
+        dist.all_reduce(stop, op=dist.ReduceOp.MAX)
+        if stop.item() > 0:
+            break
     dt = time.time() - t0
     if rank == 0:
-        q.put(dt)
+        q.put((dt, done))
     dist.destroy_process_group()
 
 
-def cpu_reference(world, batch, steps, warmup):
+def cpu_reference(world, batch, steps, warmup, budget_s=60.0):
     """Reference CPU path for this workload: W processes, gloo process group, torch DDP default
     reducer, ResNet-50, bf16 autocast, synthetic images.  Returns (images/s, seconds/step, cores)."""
     import socket
@@ -303,13 +326,14 @@ def cpu_reference(world, batch, steps, warmup):
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_cpu_worker, args=(r, world, port, batch, steps, warmup, threads, q)) for r in range(world)]
+    use_bf16 = cpu_has_bf16()
+    procs = [ctx.Process(target=_cpu_worker, args=(r, world, port, batch, steps, warmup, threads, q, use_bf16, budget_s)) for r in range(world)]
     for p in procs:
         p.start()
-    dt = q.get(timeout=1200)
+    dt, done = q.get(timeout=budget_s * 4 + 120)
     for p in procs:
         p.join(timeout=60)
-    return world * batch * steps / dt, dt / steps, threads * world
+    return world * batch * done / dt, dt / done, threads * world, done, ("bf16 autocast" if use_bf16 else "fp32 (host CPU has no bf16 units)")
 
 
 def run_reference(args):
@@ -318,11 +342,11 @@ def run_reference(args):
         return
     world = max(1, args.gpus)
     batch = int(os.environ.get("BENCH_CPU_BATCH", 16))  # bounded sample: small per-worker batch
-    ips, sps, cores = cpu_reference(world, batch, args.steps, args.warmup)
-    sample = f"{world} gloo worker(s) x batch {batch}, {args.steps} steps after {args.warmup} warm-up, torch DDP default reducer"
+    ips, sps, cores, done, cpu_dtype = cpu_reference(world, batch, args.steps, args.warmup, budget_s=float(os.environ.get("BENCH_CPU_BUDGET_S", 150)))
+    sample = f"{world} gloo worker(s) x batch {batch}, {done} steps after <= {args.warmup} warm-up, torch DDP default reducer, {cpu_dtype}"
     print(json.dumps({
         "impl": "reference", "metric": "resnet50_ddp_train_images_per_sec", "value": round(ips, 2), "unit": "images/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sps * 1e3, 2),
+        "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": round(sps * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "ResNet-50 DDP training step, synthetic 3x224x224 images, SGD, bf16 autocast; reference CPU path "
                                "(torch DDP over gloo, what ray.train.torch.TorchConfig selects without GPUs)",
@@ -372,9 +396,11 @@ def main():
     y = y_host.to(device, non_blocking=True)
     x_host_cl = x_host.contiguous(memory_format=torch.channels_last).pin_memory()
 
+    log(f"model ready, B={B}, world={world}; warm-up")
     sampler = ClockSampler(local).start() if rank == 0 else None
     for _ in range(max(3, args.warmup)):
         step(x, y)
+    log("timing device-resident steps")
     # ---- device-resident inputs
     state.time_kernels = True
     state.events = []
@@ -383,6 +409,7 @@ def main():
     launches = N.launch_count() - l0
     ktimes = state.kernel_times_ms()
     state.time_kernels = False
+    log("timing end-to-end steps")
     # ---- end to end: inputs from pinned host memory every step, loss read back every step
     ms_e2e, win2, last_loss = timed_steps(step, x, y, args.steps, dist, world, pinned=(x_host_cl, y_host))
     value = world * B * args.steps / (ms / 1e3)
@@ -390,6 +417,7 @@ def main():
 
     # ---- stock DDP reducer over NCCL on the same box (B-DDP baseline)
     nccl_ddp = None
+    log("stock NCCL DDP baseline")
     if not args.no_nccl_ddp:
         from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
         from torch.nn.parallel import DistributedDataParallel
@@ -407,11 +435,16 @@ def main():
 
     # ---- allreduce sweep
     sweep = None
+    log("allreduce sweep")
     if not args.no_sweep:
         del model, opt, step
         torch.cuda.empty_cache()
         if world > 1:
-            sweep = run_sweep_multi(state.comm, dist, world, args.sweep_max_bytes)
+            from ant_ray_b200.b200_group import PeerMemoryComm, next_comm_key
+
+            sweep_comm = PeerMemoryComm(world, rank, next_comm_key("bench-sweep"), local)  # default (full-size) grid
+            sweep = run_sweep_multi(sweep_comm, dist, world, args.sweep_max_bytes)
+            sweep_comm.destroy()
         elif rank == 0:
             sweep = run_sweep_loopback(args.sweep_max_bytes)
 
@@ -450,9 +483,10 @@ def main():
         cpu_baseline = None
         if world == 1:
             cb = int(os.environ.get("BENCH_CPU_BATCH", 16))
-            ips, sps, cores = cpu_reference(1, cb, 3, 1)
+            log("cpu baseline (bounded sample) ...")
+            ips, sps, cores, done, cpu_dtype = cpu_reference(1, cb, 3, 1, budget_s=float(os.environ.get("BENCH_CPU_BUDGET_S", 45)))
             cpu_baseline = {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": "port",
-                            "sample": f"1 gloo worker x batch {cb}, 3 steps after 1 warm-up (torch DDP default reducer, bf16 autocast, CPU)"}
+                            "sample": f"1 gloo worker x batch {cb}, {done} steps after 1 warm-up (torch DDP default reducer, {cpu_dtype}, host CPU)"}
         hook_total = sum(t for t, _ in ktimes) / max(1, args.steps)
         out = {
             "metric": "resnet50_ddp_train_images_per_sec", "value": round(value, 1), "unit": "images/s", "n_gpus": world,

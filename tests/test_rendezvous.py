@@ -1,0 +1,103 @@
+"""Host-side rendezvous plumbing (no GPU): stores, fd passing over SCM_RIGHTS, world_size-2
+exchange through real processes."""
+import os
+import threading
+
+import pytest
+
+from mini_actor import get, spawn
+
+from ant_ray_b200 import rendezvous as R
+
+
+def test_filestore_set_get_delete(tmp_path):
+    s = R.FileStore(str(tmp_path))
+    s.set("a/b/0", b"hello")
+    assert s.get("a/b/0", 1) == b"hello"
+    s.delete("a/b/0")
+    with pytest.raises(R.RendezvousTimeout):
+        s.get("a/b/0", 0.05)
+
+
+def test_filestore_get_blocks_until_set(tmp_path):
+    s = R.FileStore(str(tmp_path))
+    threading.Timer(0.1, lambda: s.set("k", b"v")).start()
+    assert s.get("k", 5) == b"v"
+
+
+def test_torchstore_adapter(tmp_path):
+    import torch.distributed as dist
+
+    ts = R.TorchStore(dist.FileStore(str(tmp_path / "f"), 1))
+    ts.set("x", b"1")
+    assert ts.get("x", 1) == b"1"
+    with pytest.raises(R.RendezvousTimeout):
+        ts.get("missing", 0.2)
+
+
+def test_default_store_from_env(tmp_path, monkeypatch):
+    monkeypatch.setenv("B200COLL_STORE", f"file://{tmp_path}")
+    assert isinstance(R.default_store(), R.FileStore)
+    monkeypatch.setenv("B200COLL_STORE", "bogus://x")
+    with pytest.raises(ValueError):
+        R.default_store()
+    monkeypatch.delenv("B200COLL_STORE")
+    with pytest.raises(RuntimeError):
+        R.default_store()
+
+
+def test_fd_passing_same_process():
+    server = R.FdServer()
+    r, w = os.pipe()
+    try:
+        server.offer(0, b"payload-bytes", r)
+        data, fd = R.fetch_fd(server.address, 1, 0, 5)
+        assert data == b"payload-bytes"
+        os.write(w, b"through the duplicated descriptor")
+        assert os.read(fd, 100) == b"through the duplicated descriptor"
+        os.close(fd)
+    finally:
+        server.close()
+        os.close(r)
+        os.close(w)
+
+
+class _Peer:
+    """One rank of a world_size-2 exchange: publishes a socket address through the store, serves a
+    memfd to the other rank and fetches the other rank's memfd (the shape of establish())."""
+
+    def __init__(self, rank, store_dir):
+        self.rank, self.store = rank, R.FileStore(store_dir)
+
+    def exchange(self):
+        fd = os.memfd_create(f"rank{self.rank}")
+        os.write(fd, f"arena of rank {self.rank}".encode())
+        server = R.FdServer()
+        try:
+            server.offer(0, f"export-{self.rank}".encode(), fd)
+            addrs = R._barrier(self.store, "t", "addr", self.rank, 2, 30, server.address.encode())
+            data, pfd = R.fetch_fd(addrs[1 - self.rank], self.rank, 0, 30)
+            os.lseek(pfd, 0, os.SEEK_SET)
+            content = os.read(pfd, 100).decode()
+            os.close(pfd)
+            R._barrier(self.store, "t", "done", self.rank, 2, 30)
+            return data.decode(), content
+        finally:
+            server.close()
+            os.close(fd)
+
+
+def test_fd_exchange_between_two_processes(store_dir):
+    actors = [spawn(_Peer, r, store_dir) for r in range(2)]
+    try:
+        res = get([a.exchange.remote() for a in actors])
+        assert res[0] == ("export-1", "arena of rank 1")
+        assert res[1] == ("export-0", "arena of rank 0")
+    finally:
+        for a in actors:
+            a.kill()
+
+
+def test_barrier_times_out_when_a_rank_is_missing(tmp_path):
+    with pytest.raises(R.RendezvousTimeout):
+        R._barrier(R.FileStore(str(tmp_path)), "p", "x", 0, 2, 0.1)

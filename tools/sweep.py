@@ -1,0 +1,146 @@
+"""Collective micro-benchmark: ours (per algorithm) next to stock NCCL, same processes, same buffers.
+
+Launch under torchrun:  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/sweep.py [opts]
+  --algos auto,oneshot,twoshot,nvls,nvls_sym   which of our paths to time
+  --sizes 1024,...    bytes (default 1 KB .. 1 GB x4)
+  --dtype f32|bf16
+  --ops allreduce,allgather,reducescatter,broadcast,sendrecv
+Prints one JSON object (rank 0).  nccl-tests conventions: algBW = S/t, busBW = algBW * 2(W-1)/W (allreduce).
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ant_ray_b200 import _native as N  # noqa: E402
+from ant_ray_b200.b200_group import PeerMemoryComm, make_config  # noqa: E402
+
+
+def timeit(fn, bufs, iters, world):
+    for i in range(min(5, iters)):
+        fn(bufs[i % len(bufs)])
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(bufs[i % len(bufs)])
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e3 / iters], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--algos", default="auto,oneshot,twoshot,nvls,nvls_sym")
+    ap.add_argument("--sizes", default="")
+    ap.add_argument("--max-bytes", type=int, default=1 << 30)
+    ap.add_argument("--dtype", default="f32")
+    ap.add_argument("--ops", default="allreduce")
+    ap.add_argument("--max-blocks", type=int, default=0)
+    ap.add_argument("--staging-mb", type=int, default=256)
+    ap.add_argument("--no-nccl", action="store_true")
+    a = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dtype = {"f32": torch.float32, "bf16": torch.bfloat16}[a.dtype]
+    nat = {"f32": N.FLOAT32, "bf16": N.BFLOAT16}[a.dtype]
+    esz = 4 if a.dtype == "f32" else 2
+    sizes = [int(s) for s in a.sizes.split(",")] if a.sizes else [1024 * 4**k for k in range(11) if 1024 * 4**k <= a.max_bytes]
+    kw = dict(staging_bytes=a.staging_mb << 20, symmetric_bytes=max(sizes) if "nvls_sym" in a.algos else 0)
+    if a.max_blocks:
+        kw["max_blocks"] = a.max_blocks
+    comm = PeerMemoryComm(world, rank, "sweep", local, None, make_config(**kw))
+    algos = {"auto": N.ALGO_AUTO, "oneshot": N.ALGO_ONESHOT, "twoshot": N.ALGO_TWOSHOT, "nvls": N.ALGO_NVLS, "nvls_sym": N.ALGO_NVLS}
+    out = {"world": world, "dtype": a.dtype, "multicast": bool(comm.multicast), "nccl_version": ".".join(map(str, torch.cuda.nccl.version())),
+           "max_blocks": comm.config.max_blocks, "rows": []}
+    k = 2 * (world - 1) / world
+    for op in a.ops.split(","):
+        for size in sizes:
+            n = size // esz
+            nbuf = max(1, min(16, (256 << 20) // size))
+            iters = 200 if size <= (1 << 20) else (40 if size <= (64 << 20) else 10)
+            row = {"op": op, "bytes": size}
+            if op == "allreduce":
+                bufs = [torch.ones(n, dtype=dtype, device="cuda") for _ in range(nbuf)]
+                for name in a.algos.split(","):
+                    if name in ("nvls", "nvls_sym") and not comm.multicast:
+                        continue
+                    if name == "oneshot" and size * world > (a.staging_mb << 20) * 4:
+                        continue
+                    if name == "nvls_sym":
+                        sb = [comm.symmetric_tensor((n,), dtype)]
+                        us = timeit(lambda b: comm.allreduce(b.data_ptr(), b.data_ptr(), n, nat, N.SUM, N.ALGO_NVLS), sb, iters, world)
+                    else:
+                        us = timeit(lambda b: comm.allreduce(b.data_ptr(), b.data_ptr(), n, nat, N.SUM, algos[name]), bufs, iters, world)
+                    row[name + "_us"] = round(us, 2)
+                    row[name + "_busbw"] = round(size / us / 1e3 * k, 1)
+                if not a.no_nccl:
+                    us = timeit(lambda b: dist.all_reduce(b), bufs, iters, world)
+                    row["nccl_us"] = round(us, 2); row["nccl_busbw"] = round(size / us / 1e3 * k, 1)
+            elif op == "allgather":
+                bufs = [torch.ones(n, dtype=dtype, device="cuda") for _ in range(nbuf)]
+                outs = [torch.empty(n, dtype=dtype, device="cuda") for _ in range(world)]
+                flat = torch.empty(n * world, dtype=dtype, device="cuda")
+                ptrs = [o.data_ptr() for o in outs]
+                us = timeit(lambda b: comm.allgather(b.data_ptr(), ptrs, n, nat), bufs, iters, world)
+                row["b200_us"] = round(us, 2); row["b200_busbw"] = round(size * world / us / 1e3 * (world - 1) / world, 1)
+                if not a.no_nccl:
+                    # what the reference does: allGather into a flat buffer, then W copies (nccl_collective_group.py:278-296)
+                    def ref(b):
+                        dist.all_gather_into_tensor(flat, b)
+                        for j in range(world):
+                            outs[j].copy_(flat[j * n:(j + 1) * n])
+                    us = timeit(ref, bufs, iters, world)
+                    row["nccl_ref_us"] = round(us, 2); row["nccl_ref_busbw"] = round(size * world / us / 1e3 * (world - 1) / world, 1)
+            elif op == "reducescatter":
+                lists = [torch.ones(n, dtype=dtype, device="cuda") for _ in range(world)]
+                o = torch.empty(n, dtype=dtype, device="cuda")
+                flat = torch.empty(n * world, dtype=dtype, device="cuda")
+                ptrs = [t.data_ptr() for t in lists]
+                us = timeit(lambda b: comm.reducescatter(ptrs, o.data_ptr(), n, nat, N.SUM), [None], iters, world)
+                row["b200_us"] = round(us, 2); row["b200_busbw"] = round(size * world / us / 1e3 * (world - 1) / world, 1)
+                if not a.no_nccl:
+                    def ref(b):
+                        for j in range(world):
+                            flat[j * n:(j + 1) * n].copy_(lists[j])
+                        dist.reduce_scatter_tensor(o, flat)
+                    us = timeit(ref, [None], iters, world)
+                    row["nccl_ref_us"] = round(us, 2); row["nccl_ref_busbw"] = round(size * world / us / 1e3 * (world - 1) / world, 1)
+            elif op == "broadcast":
+                bufs = [torch.ones(n, dtype=dtype, device="cuda") for _ in range(nbuf)]
+                us = timeit(lambda b: comm.broadcast(b.data_ptr(), n, nat, 0), bufs, iters, world)
+                row["b200_us"] = round(us, 2); row["b200_busbw"] = round(size / us / 1e3, 1)
+                if not a.no_nccl:
+                    us = timeit(lambda b: dist.broadcast(b, 0), bufs, iters, world)
+                    row["nccl_us"] = round(us, 2); row["nccl_busbw"] = round(size / us / 1e3, 1)
+            elif op == "sendrecv":
+                bufs = [torch.ones(n, dtype=dtype, device="cuda") for _ in range(nbuf)]
+                def ours(b):
+                    if rank == 0: comm.send(b.data_ptr(), size, 1)
+                    elif rank == 1: comm.recv(b.data_ptr(), size, 0)
+                us = timeit(ours, bufs, iters, world)
+                row["b200_us"] = round(us, 2); row["b200_gbps"] = round(size / us / 1e3, 1)
+                if not a.no_nccl:
+                    def ref(b):
+                        if rank == 0: dist.send(b, 1)
+                        elif rank == 1: dist.recv(b, 0)
+                    us = timeit(ref, bufs, iters, world)
+                    row["nccl_us"] = round(us, 2); row["nccl_gbps"] = round(size / us / 1e3, 1)
+            out["rows"].append(row)
+            if rank == 0:
+                print("#", json.dumps(row), flush=True)
+    comm.check()
+    if rank == 0:
+        print(json.dumps(out))
+    comm.destroy()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
