@@ -506,6 +506,20 @@ extern "C" int b200c_comm_destroy(b200c_comm_t* c) {
   return B200C_OK;
 }
 
+extern "C" int b200c_debug_fill_flags(b200c_comm_t* c, uint32_t value) {
+  if (!c || c->destroyed) return fail(B200C_ESTATE, "communicator destroyed");
+  DeviceGuard g(c->device);
+  RT(cudaDeviceSynchronize());
+  static_assert(kPadUsed % 4 == 0, "pad is u32 words");
+  uint32_t* host = new uint32_t[kPadUsed / 4];
+  for (size_t i = 0; i < kPadUsed / 4; i++) host[i] = value;
+  for (size_t i = kOffOpSig / 4; i < kOffOpSig / 4 + 16; i++) host[i] = 0xFFFFFFFFu;  // signature wildcard
+  cudaError_t e = cudaMemcpy(c->arena[c->rank], host, kPadUsed, cudaMemcpyHostToDevice);
+  delete[] host;
+  if (e != cudaSuccess) return fail(B200C_ECUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
+  return B200C_OK;
+}
+
 extern "C" int b200c_comm_rank(const b200c_comm_t* c) { return c ? c->rank : -1; }
 extern "C" int b200c_comm_world(const b200c_comm_t* c) { return c ? c->world : -1; }
 extern "C" int b200c_comm_has_multicast(const b200c_comm_t* c) { return c && c->mc_arena ? 1 : 0; }
@@ -543,7 +557,7 @@ static uint32_t make_sig(int opcode, int dtype, int op, size_t n, int root, int 
   uint64_t h = 1469598103934665603ull;
   uint64_t v[6] = {(uint64_t)opcode, (uint64_t)dtype, (uint64_t)op, (uint64_t)n, (uint64_t)(root + 1), (uint64_t)extra};
   for (int i = 0; i < 6; i++) { h ^= v[i]; h *= 1099511628211ull; }
-  return (uint32_t)(h ^ (h >> 32)) | 1u;
+  return ((uint32_t)(h ^ (h >> 32)) & 0x7fffffffu) | 1u;  // never 0 and never the 0xFFFFFFFF wildcard
 }
 static void base_args(b200c_comm* c, CollArgs* a) {
   memset(a, 0, sizeof *a);

@@ -50,6 +50,7 @@ def parse():
     p.add_argument("--wire", default=os.environ.get("BENCH_WIRE", "bf16"), choices=["bf16", "fp32", "fp16"])
     p.add_argument("--no-sweep", action="store_true")
     p.add_argument("--no-nccl-ddp", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--sweep-max-bytes", type=int, default=int(os.environ.get("BENCH_SWEEP_MAX", 1 << 30)))
     return p.parse_args()
 
@@ -266,6 +267,24 @@ def run_sweep_loopback(max_bytes):
 # ------------------------------------------------------------------------------------------------
 # reference CPU path: torch DDP over gloo on the host cores (bounded sample)
 # ------------------------------------------------------------------------------------------------
+def effective_cores():
+    """Host cores this container may actually use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(quota) // int(period)))
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // p))
+        except (OSError, ValueError):
+            pass
+    return n
+
+
 def cpu_has_bf16():
     try:
         flags = open("/proc/cpuinfo").read()
@@ -319,7 +338,7 @@ def cpu_reference(world, batch, steps, warmup, budget_s=60.0):
 
     import torch.multiprocessing as mp
 
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     threads = max(1, cores // world)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -405,7 +424,11 @@ def main():
     state.time_kernels = True
     state.events = []
     l0 = N.launch_count()
+    if os.environ.get("BENCH_CUDA_PROFILER") == "1":  # ncu --profile-from-start off: capture the timed region only
+        torch.cuda.profiler.start()
     ms, win1, _ = timed_steps(step, x, y, args.steps, dist, world)
+    if os.environ.get("BENCH_CUDA_PROFILER") == "1":
+        torch.cuda.profiler.stop()
     launches = N.launch_count() - l0
     ktimes = state.kernel_times_ms()
     state.time_kernels = False
@@ -481,7 +504,7 @@ def main():
         else:
             roofline = None
         cpu_baseline = None
-        if world == 1:
+        if world == 1 and not args.no_cpu_baseline:
             cb = int(os.environ.get("BENCH_CPU_BATCH", 16))
             log("cpu baseline (bounded sample) ...")
             ips, sps, cores, done, cpu_dtype = cpu_reference(1, cb, 3, 1, budget_s=float(os.environ.get("BENCH_CPU_BUDGET_S", 45)))

@@ -89,7 +89,7 @@ typedef struct {
   uint64_t symmetric_bytes;    /* user-visible symmetric region (0 = none) */
   uint64_t p2p_slot_bytes;     /* bytes of one p2p ring slot */
   uint32_t p2p_slots;          /* ring slots per ordered (src,dst) pair */
-  uint32_t max_blocks;         /* upper bound on CTAs per collective kernel (<= 1024) */
+  uint32_t max_blocks;         /* upper bound on CTAs per collective kernel (<= 2048) */
   uint64_t oneshot_max_bytes;  /* AUTO: message <= this -> one-shot */
   uint64_t nvls_min_bytes;     /* AUTO: message >= this and multicast bound -> NVLS */
   uint64_t timeout_ms;         /* device-side bounded spin; 0 = default (30 s) */
@@ -211,6 +211,13 @@ int b200c_recv(b200c_comm_t* comm, void* buf, size_t bytes, int peer, b200c_stre
 
 /* barrier: nccl_collective_group.py:192-210 (an allreduce of [1] in the reference). */
 int b200c_barrier(b200c_comm_t* comm, b200c_stream_t stream);
+
+/* Profiling aid: set every flag of this rank's signal pad to `value`.  With value = 0x7fffffff every
+ * wait of every later op is already satisfied, so ONE rank's kernel can run without its peers —
+ * which is what Nsight Compute's kernel replay needs (it re-runs a kernel in isolation, so a kernel
+ * that waits for a concurrently running peer kernel would never finish).  Results are garbage;
+ * memory traffic and instruction mix are those of the real run.  Never call it on a live group. */
+int b200c_debug_fill_flags(b200c_comm_t* comm, uint32_t value);
 
 /* Launch statistics (bench.py's gpu_launches claim). */
 uint64_t b200c_launch_count(void);

@@ -20,10 +20,26 @@ from ant_ray_b200 import _native as N  # noqa: E402
 from ant_ray_b200.b200_group import PeerMemoryComm, make_config  # noqa: E402
 
 
+PER_ITER = False
+LAST_STATS = {}
+
+
 def timeit(fn, bufs, iters, world):
+    """Mean microseconds per call over a back-to-back loop (nccl-tests style), max over ranks.
+    With --per-iter every call is bracketed by its own events and LAST_STATS gets min/median/max."""
     for i in range(min(5, iters)):
         fn(bufs[i % len(bufs)])
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    if PER_ITER:
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for i, (a, b) in enumerate(evs):
+            a.record(); fn(bufs[i % len(bufs)]); b.record()
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
+        t = torch.tensor([ts[len(ts) // 2], ts[0], ts[-1], sum(ts) / len(ts)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        LAST_STATS.update(median=round(t[0].item(), 2), min=round(t[1].item(), 2), max=round(t[2].item(), 2))
+        return t[3].item()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(iters):
@@ -44,7 +60,12 @@ def main():
     ap.add_argument("--max-blocks", type=int, default=0)
     ap.add_argument("--staging-mb", type=int, default=256)
     ap.add_argument("--no-nccl", action="store_true")
+    ap.add_argument("--per-iter", action="store_true", help="time every call separately; report min/median/max")
+    ap.add_argument("--blocks-list", default="", help="extra communicators with these max_blocks, e.g. 592,1184")
+    ap.add_argument("--hybrid", default="", help="fractions of the message sent through two-shot P2P while NVLS takes the rest, e.g. 0.2,0.3")
     a = ap.parse_args()
+    global PER_ITER
+    PER_ITER = a.per_iter
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -56,6 +77,14 @@ def main():
     if a.max_blocks:
         kw["max_blocks"] = a.max_blocks
     comm = PeerMemoryComm(world, rank, "sweep", local, None, make_config(**kw))
+    extra = {}
+    for mb in [int(x) for x in a.blocks_list.split(",") if x]:
+        extra[mb] = PeerMemoryComm(world, rank, f"sweep-mb{mb}", local, None, make_config(**{**kw, "max_blocks": mb}))
+    hyb = None
+    if a.hybrid:
+        hyb = (PeerMemoryComm(world, rank, "sweep-hyb-a", local, None, make_config(**kw)),
+               PeerMemoryComm(world, rank, "sweep-hyb-b", local, None, make_config(**kw)),
+               torch.cuda.Stream(), torch.cuda.Stream())
     algos = {"auto": N.ALGO_AUTO, "oneshot": N.ALGO_ONESHOT, "twoshot": N.ALGO_TWOSHOT, "nvls": N.ALGO_NVLS, "nvls_sym": N.ALGO_NVLS}
     out = {"world": world, "dtype": a.dtype, "multicast": bool(comm.multicast), "nccl_version": ".".join(map(str, torch.cuda.nccl.version())),
            "max_blocks": comm.config.max_blocks, "rows": []}
@@ -80,6 +109,30 @@ def main():
                         us = timeit(lambda b: comm.allreduce(b.data_ptr(), b.data_ptr(), n, nat, N.SUM, algos[name]), bufs, iters, world)
                     row[name + "_us"] = round(us, 2)
                     row[name + "_busbw"] = round(size / us / 1e3 * k, 1)
+                    if PER_ITER:
+                        row[name + "_stats"] = dict(LAST_STATS)
+                for mb, cx in extra.items():
+                    for name in ("twoshot", "nvls"):
+                        if name not in a.algos.split(",") or (name == "nvls" and not cx.multicast):
+                            continue
+                        us = timeit(lambda b: cx.allreduce(b.data_ptr(), b.data_ptr(), n, nat, N.SUM, algos[name]), bufs, iters, world)
+                        row[f"{name}_mb{mb}_us"] = round(us, 2); row[f"{name}_mb{mb}_busbw"] = round(size / us / 1e3 * k, 1)
+                if hyb is not None and comm.multicast and size >= (16 << 20):
+                    ca, cb, sa, sb2 = hyb
+                    for f in [float(x) for x in a.hybrid.split(",")]:
+                        n2 = int(n * f) // 1024 * 1024
+                        n1 = n - n2
+
+                        def both(b):
+                            cur = torch.cuda.current_stream()
+                            sa.wait_stream(cur); sb2.wait_stream(cur)
+                            with torch.cuda.stream(sa):
+                                ca.allreduce(b.data_ptr(), b.data_ptr(), n1, nat, N.SUM, N.ALGO_NVLS)
+                            with torch.cuda.stream(sb2):
+                                cb.allreduce(b.data_ptr() + n1 * esz, b.data_ptr() + n1 * esz, n2, nat, N.SUM, N.ALGO_TWOSHOT)
+                            cur.wait_stream(sa); cur.wait_stream(sb2)
+                        us = timeit(both, bufs, iters, world)
+                        row[f"hybrid{f}_us"] = round(us, 2); row[f"hybrid{f}_busbw"] = round(size / us / 1e3 * k, 1)
                 if not a.no_nccl:
                     us = timeit(lambda b: dist.all_reduce(b), bufs, iters, world)
                     row["nccl_us"] = round(us, 2); row["nccl_busbw"] = round(size / us / 1e3 * k, 1)
@@ -136,6 +189,10 @@ def main():
             if rank == 0:
                 print("#", json.dumps(row), flush=True)
     comm.check()
+    for cx in extra.values():
+        cx.check(); cx.destroy()
+    if hyb is not None:
+        hyb[0].destroy(); hyb[1].destroy()
     if rank == 0:
         print(json.dumps(out))
     comm.destroy()
