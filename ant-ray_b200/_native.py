@@ -29,7 +29,7 @@ INT8, UINT8, INT32, UINT32, INT64, UINT64, FLOAT16, FLOAT32, FLOAT64, BFLOAT16 =
 # b200c_redop_t (ncclRedOp_t numbering)
 SUM, PROD, MAX, MIN, AVG = range(5)
 # b200c_algo_t
-ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS = range(4)
+ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS, ALGO_NVLS_PIPE = range(5)
 # b200c_share_mode_t
 SHARE_VMM_FD, SHARE_LEGACY_IPC = 0, 1
 MAX_RANKS = 8
@@ -39,7 +39,7 @@ class Config(Structure):
     _fields_ = [("struct_size", c_uint32), ("share_mode", c_int32), ("staging_bytes", c_uint64),
                 ("symmetric_bytes", c_uint64), ("p2p_slot_bytes", c_uint64), ("p2p_slots", c_uint32),
                 ("max_blocks", c_uint32), ("oneshot_max_bytes", c_uint64), ("nvls_min_bytes", c_uint64),
-                ("timeout_ms", c_uint64)]
+                ("nvls_pipe_min_bytes", c_uint64), ("timeout_ms", c_uint64)]
 
 
 class Props(Structure):

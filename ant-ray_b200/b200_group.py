@@ -126,6 +126,7 @@ def make_config(**overrides):
         "B200COLL_MAX_BLOCKS": ("max_blocks", int),
         "B200COLL_ONESHOT_MAX_BYTES": ("oneshot_max_bytes", int),
         "B200COLL_NVLS_MIN_BYTES": ("nvls_min_bytes", int),
+        "B200COLL_NVLS_PIPE_MIN_BYTES": ("nvls_pipe_min_bytes", int),
         "B200COLL_TIMEOUT_MS": ("timeout_ms", int),
         "B200COLL_P2P_SLOT_BYTES": ("p2p_slot_bytes", int),
         "B200COLL_P2P_SLOTS": ("p2p_slots", int),

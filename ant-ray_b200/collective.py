@@ -189,86 +189,86 @@ def get_collective_group_size(group_name: str = "default") -> int:
         return _group_mgr.get_group_by_name(group_name).world_size
 
 
+def _options(cls, **fields):
+    opts = cls()
+    for name, value in fields.items():
+        setattr(opts, name, value)
+    return opts
+
+
+def _peer_rank(g, rank: int, what: str) -> int:
+    """Validate a peer rank for p2p (ValueError out of range, RuntimeError for self)."""
+    _check_rank_valid(g, rank)
+    if rank == g.rank:
+        raise RuntimeError("The {} rank '{}' is self.".format(what, rank))
+    return rank
+
+
+def _full_list(g, tensor_list, op_name: str):
+    _check_tensor_list_input(tensor_list)
+    if len(tensor_list) != g.world_size:
+        raise RuntimeError("The length of the tensor list operands to {} must be equal to world_size.".format(op_name))
+    return tensor_list
+
+
 def allreduce(tensor, group_name: str = "default", op=types.ReduceOp.SUM):
-    """In-place allreduce of `tensor` across the group."""
+    """Reduce `tensor` across the group; every member ends up with the result, in place."""
     _check_single_tensor_input(tensor)
-    g = get_group_handle(group_name)
-    opts = types.AllReduceOptions()
-    opts.reduceOp = op
-    g.allreduce([tensor], opts)
+    get_group_handle(group_name).allreduce([tensor], _options(types.AllReduceOptions, reduceOp=op))
 
 
 def barrier(group_name: str = "default"):
-    g = get_group_handle(group_name)
-    g.barrier()
+    """Block until every member of the group has reached the barrier."""
+    get_group_handle(group_name).barrier()
 
 
 def reduce(tensor, dst_rank: int = 0, group_name: str = "default", op=types.ReduceOp.SUM):
+    """Reduce `tensor` across the group onto `dst_rank` (other members keep their input)."""
     _check_single_tensor_input(tensor)
     g = get_group_handle(group_name)
     _check_rank_valid(g, dst_rank)
-    opts = types.ReduceOptions()
-    opts.reduceOp = op
-    opts.root_rank = dst_rank
-    opts.root_tensor = 0
-    g.reduce([tensor], opts)
+    g.reduce([tensor], _options(types.ReduceOptions, reduceOp=op, root_rank=dst_rank, root_tensor=0))
 
 
 def broadcast(tensor, src_rank: int = 0, group_name: str = "default"):
+    """Copy `src_rank`'s tensor into every member's tensor."""
     _check_single_tensor_input(tensor)
     g = get_group_handle(group_name)
     _check_rank_valid(g, src_rank)
-    opts = types.BroadcastOptions()
-    opts.root_rank = src_rank
-    opts.root_tensor = 0
-    g.broadcast([tensor], opts)
+    g.broadcast([tensor], _options(types.BroadcastOptions, root_rank=src_rank, root_tensor=0))
 
 
 def allgather(tensor_list: list, tensor, group_name: str = "default"):
+    """Gather every member's `tensor` into `tensor_list` (one slot per rank) on every member."""
     _check_single_tensor_input(tensor)
-    _check_tensor_list_input(tensor_list)
     g = get_group_handle(group_name)
-    if len(tensor_list) != g.world_size:
-        raise RuntimeError("The length of the tensor list operands to allgather must be equal to world_size.")
-    g.allgather([tensor_list], [tensor], types.AllGatherOptions())
+    g.allgather([_full_list(g, tensor_list, "allgather")], [tensor], types.AllGatherOptions())
 
 
 def reducescatter(tensor, tensor_list: list, group_name: str = "default", op=types.ReduceOp.SUM):
+    """Reduce the members' `tensor_list`s slot by slot; member r receives slot r in `tensor`."""
     _check_single_tensor_input(tensor)
-    _check_tensor_list_input(tensor_list)
     g = get_group_handle(group_name)
-    opts = types.ReduceScatterOptions()
-    opts.reduceOp = op
-    if len(tensor_list) != g.world_size:
-        raise RuntimeError("The length of the tensor list operands to reducescatter must be equal to world_size.")
-    g.reducescatter([tensor], [tensor_list], opts)
+    g.reducescatter([tensor], [_full_list(g, tensor_list, "reducescatter")], _options(types.ReduceScatterOptions, reduceOp=op))
 
 
 def send(tensor, dst_rank: int, group_name: str = "default"):
+    """Send `tensor` to `dst_rank` (pairs with a recv on that member)."""
     _check_single_tensor_input(tensor)
     g = get_group_handle(group_name)
-    _check_rank_valid(g, dst_rank)
-    if dst_rank == g.rank:
-        raise RuntimeError("The destination rank '{}' is self.".format(dst_rank))
-    opts = types.SendOptions()
-    opts.dst_rank = dst_rank
-    g.send([tensor], opts)
+    g.send([tensor], _options(types.SendOptions, dst_rank=_peer_rank(g, dst_rank, "destination")))
 
 
 def recv(tensor, src_rank: int, group_name: str = "default"):
+    """Receive into `tensor` from `src_rank`."""
     _check_single_tensor_input(tensor)
     g = get_group_handle(group_name)
-    _check_rank_valid(g, src_rank)
-    if src_rank == g.rank:
-        raise RuntimeError("The destination rank '{}' is self.".format(src_rank))
-    opts = types.RecvOptions()
-    opts.src_rank = src_rank
-    g.recv([tensor], opts)
+    g.recv([tensor], _options(types.RecvOptions, src_rank=_peer_rank(g, src_rank, "source")))
 
 
 def _multigpu_unsupported(*_args, **_kwargs):
-    """The reference's *_multigpu calls drive several GPUs from one process
-    (collective.py:346-366 etc.).  This backend is one process per GPU by design."""
+    """The reference's *_multigpu calls drive several GPUs from one process.  This backend is one
+    process per GPU by design."""
     raise RuntimeError("Multigpu calls are not supported by the B200 backend: run one process (actor) per GPU.")
 
 

@@ -146,6 +146,7 @@ struct b200c_comm {
   // state
   bool ready = false, destroyed = false;
   uint32_t seq = 0;
+  uint32_t pipe_base = 0;  // flag epoch of the pipelined kernels (advanced by the sub-tile count of each op)
   uint32_t send_cells[kMaxRanks] = {};
   uint32_t recv_cells[kMaxRanks] = {};
   DevComm dev{};
@@ -190,7 +191,8 @@ extern "C" void b200c_default_config(b200c_config_t* cfg) {
   cfg->p2p_slots = 256;
   cfg->max_blocks = 296;
   cfg->oneshot_max_bytes = 0;  // 0 = pick by world size in b200c_comm_create
-  cfg->nvls_min_bytes = 1ull << 20;
+  cfg->nvls_min_bytes = (1ull << 20) + 1;
+  cfg->nvls_pipe_min_bytes = 0;  // off by default until validated on the target box
   cfg->timeout_ms = 30000;
 }
 
@@ -269,7 +271,8 @@ extern "C" int b200c_comm_create(int rank, int world, int device, const b200c_co
   if (cfg.p2p_slot_bytes < 512 || cfg.p2p_slot_bytes % 16) return fail(B200C_EINVAL, "p2p_slot_bytes must be a multiple of 16 and >= 512");
   if (cfg.staging_bytes < (1u << 16) || cfg.staging_bytes % 4096) return fail(B200C_EINVAL, "staging_bytes must be a multiple of 4096 and >= 64 KiB");
   if (cfg.timeout_ms == 0) cfg.timeout_ms = 30000;
-  if (cfg.oneshot_max_bytes == 0) cfg.oneshot_max_bytes = world <= 2 ? (8ull << 20) : (world <= 4 ? (512ull << 10) : (256ull << 10));
+  // measured crossovers (profiles/r01_sweep_*): W=2 one-shot wins to 8 MiB; W=8 one-shot 23 us vs NVLS 28 us at 1 MiB
+  if (cfg.oneshot_max_bytes == 0) cfg.oneshot_max_bytes = world <= 2 ? (8ull << 20) : (1ull << 20);
 
   int ndev = 0;
   RT(cudaGetDeviceCount(&ndev));
@@ -591,8 +594,9 @@ static void launch_mixed(int algo, const CollArgs& a, int grid, cudaStream_t s) 
   else k_allreduce_twoshot<TI, TW, B200C_SUM><<<grid, kThreads, 0, s>>>(a);
 }
 template <typename TI, typename TW>
-static void launch_nvls(const CollArgs& a, int grid, cudaStream_t s) {
-  k_allreduce_nvls<TI, TW><<<grid, kThreads, 0, s>>>(a);
+static void launch_nvls(const CollArgs& a, int grid, cudaStream_t s, bool pipe) {
+  if (pipe) k_allreduce_nvls_pipe<TI, TW><<<grid, kThreads, 0, s>>>(a);
+  else k_allreduce_nvls<TI, TW><<<grid, kThreads, 0, s>>>(a);
 }
 
 static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t count, int dtype, int wire, int op, float scale,
@@ -607,7 +611,7 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     if (!(dtype == B200C_FLOAT32 && (wire == B200C_BFLOAT16 || wire == B200C_FLOAT16))) return fail(B200C_EUNSUPPORTED, "wire dtype %d for buffer dtype %d", wire, dtype);
     if (op != B200C_SUM && op != B200C_AVG) return fail(B200C_EUNSUPPORTED, "compressed wire supports SUM/AVG only");
   }
-  if (algo < B200C_ALGO_AUTO || algo > B200C_ALGO_NVLS) return fail(B200C_EINVAL, "bad algo %d", algo);
+  if (algo < B200C_ALGO_AUTO || algo > B200C_ALGO_NVLS_PIPE) return fail(B200C_EINVAL, "bad algo %d", algo);
   if (op == B200C_AVG) { has_scale = 1; scale = 1.f / (float)c->world; }
   if (count == 0) return B200C_OK;
   DeviceGuard g(c->device);
@@ -636,7 +640,7 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
 
   const bool nvls_ok = c->mc_arena && (op == B200C_SUM || op == B200C_AVG) &&
                        (wire == B200C_FLOAT32 || wire == B200C_BFLOAT16 || wire == B200C_FLOAT16);
-  if (algo == B200C_ALGO_NVLS && !nvls_ok) return fail(B200C_EUNSUPPORTED, "NVLS needs a bound multicast object, SUM/AVG and f32/bf16/f16");
+  if ((algo == B200C_ALGO_NVLS || algo == B200C_ALGO_NVLS_PIPE) && !nvls_ok) return fail(B200C_EUNSUPPORTED, "NVLS needs a bound multicast object, SUM/AVG and f32/bf16/f16");
   const char* in = static_cast<const char*>(send);
   char* out = static_cast<char*>(recv);
   size_t done = 0;
@@ -644,6 +648,8 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     size_t left = count - done;
     size_t bytes_left = left * wsz;
     int al = algo;
+    bool pipe = false;
+    if (al == B200C_ALGO_NVLS_PIPE) { al = B200C_ALGO_NVLS; pipe = true; }
     if (al == B200C_ALGO_AUTO) {
       if (bytes_left <= c->cfg.oneshot_max_bytes) al = B200C_ALGO_ONESHOT;
       else if (nvls_ok && W > 2 && bytes_left >= c->cfg.nvls_min_bytes) al = B200C_ALGO_NVLS;
@@ -679,15 +685,23 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
       a.symmetric = sym ? 1 : 0;
       a.sym_off = sym ? (size_t)((const char*)a.in - c->arena[c->rank]) : 0;
       plan_tiles(a.chunk, wsz, vec, c->cfg.max_blocks, kMinTileBytes, &a.tile, &grid);
+      if (!sym && algo == B200C_ALGO_AUTO && c->cfg.nvls_pipe_min_bytes && n * wsz >= c->cfg.nvls_pipe_min_bytes) pipe = true;
+      if (sym) pipe = false;  // nothing to overlap: the symmetric path has no staging copies
+      if (pipe) {
+        a.sub = 8192 / wsz;  // 8 KiB sub-tiles
+        size_t kmax = (a.tile + a.sub - 1) / a.sub;
+        a.pipe_base = c->pipe_base;
+        c->pipe_base += (uint32_t)kmax;
+      }
     }
     a.n = n;
-    a.sig = make_sig(OPC_ALLREDUCE, dtype * 16 + wire, op, n, -1, al * 2 + (sym ? 1 : 0));
+    a.sig = make_sig(OPC_ALLREDUCE, dtype * 16 + wire, op, n, -1, al * 4 + (sym ? 1 : 0) + (pipe ? 2 : 0));
     if (al == B200C_ALGO_NVLS) {
-      if (dtype == B200C_FLOAT32 && wire == B200C_FLOAT32) launch_nvls<float, float>(a, grid, s);
-      else if (dtype == B200C_BFLOAT16) launch_nvls<bf16_t, bf16_t>(a, grid, s);
-      else if (dtype == B200C_FLOAT16) launch_nvls<f16_t, f16_t>(a, grid, s);
-      else if (wire == B200C_BFLOAT16) launch_nvls<float, bf16_t>(a, grid, s);
-      else launch_nvls<float, f16_t>(a, grid, s);
+      if (dtype == B200C_FLOAT32 && wire == B200C_FLOAT32) launch_nvls<float, float>(a, grid, s, pipe);
+      else if (dtype == B200C_BFLOAT16) launch_nvls<bf16_t, bf16_t>(a, grid, s, pipe);
+      else if (dtype == B200C_FLOAT16) launch_nvls<f16_t, f16_t>(a, grid, s, pipe);
+      else if (wire == B200C_BFLOAT16) launch_nvls<float, bf16_t>(a, grid, s, pipe);
+      else launch_nvls<float, f16_t>(a, grid, s, pipe);
     } else if (wire != dtype) {
       if (wire == B200C_BFLOAT16) launch_mixed<float, bf16_t>(al, a, grid, s);
       else launch_mixed<float, f16_t>(al, a, grid, s);

@@ -256,6 +256,123 @@ __global__ void __launch_bounds__(kThreads, 2) k_allreduce_nvls(CollArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pipelined staged NVLS allreduce (large plain tensors).  The CTA is split into three warp-
+// specialised roles that run concurrently on sub-tiles of the CTA's slab:
+//   IN  (192 threads): user tensor -> staging (every chunk's slice of sub-tile k), then raises
+//                      pipeA[block][rank] = base+k+1 on every rank (own pad included);
+//   RED (128 threads): waits pipeA from all W ranks, multimem.ld_reduce + multimem.st of the OWN
+//                      chunk's slice of sub-tile k, then raises pipeB the same way;
+//   OUT (192 threads): waits pipeB from all W ranks, staging -> user tensor.
+// The local HBM copies of sub-tiles k+1 / k-1 therefore overlap the switch traffic of sub-tile k,
+// instead of three back-to-back phases as in k_allreduce_nvls.  Roles talk only through the flags
+// (global memory) and synchronise internally with named barriers.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPipeIn = 192, kPipeRed = 128, kPipeOut = 192;
+static_assert(kPipeIn + kPipeRed + kPipeOut == kThreads, "roles must cover the CTA");
+
+template <typename TI, typename TW>
+__global__ void __launch_bounds__(kThreads, 2) k_allreduce_nvls_pipe(CollArgs a) {
+  const DevComm& c = a.c;
+  const int r = c.rank, W = c.world;
+  if (!coll_prologue(a)) return;
+  check_signature(a);
+  __shared__ int s_fail;
+  if (threadIdx.x == 0) s_fail = 0;
+  __syncthreads();
+  constexpr int V = 16 / sizeof(TW);
+  const size_t t0 = (size_t)blockIdx.x * a.tile;
+  const size_t t1 = (t0 + a.tile < a.chunk) ? t0 + a.tile : a.chunk;
+  if (t0 >= t1) return;
+  const int K = (int)((t1 - t0 + a.sub - 1) / a.sub);
+  const TI* in = static_cast<const TI*>(a.in);
+  TI* out = static_cast<TI*>(a.out);
+  const size_t base_off = c.off_staging + (size_t)(a.seq & 1) * c.staging_bytes;
+  TW* mine = reinterpret_cast<TW*>(c.arena[r] + base_off);
+  const size_t flag_idx = (size_t)blockIdx.x * 8;
+  const uint32_t* myA = reinterpret_cast<const uint32_t*>(c.arena[r] + kOffPipeA) + flag_idx;
+  const uint32_t* myB = reinterpret_cast<const uint32_t*>(c.arena[r] + kOffPipeB) + flag_idx;
+  const int tid = threadIdx.x;
+
+  if (tid < kPipeIn) {
+    // ------------------------------------------------------------------ IN
+    const int t = tid;
+    for (int k = 0; k < K; k++) {
+      const size_t s0 = t0 + (size_t)k * a.sub;
+      const size_t s1 = (s0 + a.sub < t1) ? s0 + a.sub : t1;
+      for (int j = 0; j < W; j++) {
+        size_t lo = (size_t)j * a.chunk + s0, hi = (size_t)j * a.chunk + s1;
+        size_t cnt = clip_count(lo, hi, a.n);
+        if (cnt) move_tile<TI, TW, false>(mine + lo, in + lo, cnt, t, kPipeIn);
+        size_t end = lo + cnt, padded = (end + V - 1) / V * V;
+        if (cnt && padded > end && padded <= hi) {
+          TW z = Traits<TW>::from_acc((typename Traits<TW>::A)0);
+          for (size_t q = end + t; q < padded; q += kPipeIn) mine[q] = z;
+        }
+      }
+      role_sync(1, kPipeIn);
+      if (t < W) st_release_sys(reinterpret_cast<uint32_t*>(c.arena[t] + kOffPipeA) + flag_idx + r, a.pipe_base + k + 1);
+    }
+  } else if (tid < kPipeIn + kPipeRed) {
+    // ------------------------------------------------------------------ RED
+    const int t = tid - kPipeIn;
+    for (int k = 0; k < K; k++) {
+      if (t < W && !wait_flag(myA + t, a.pipe_base + k + 1, c, t, 1)) s_fail = 1;
+      role_sync(2, kPipeRed);
+      if (s_fail) return;
+      const size_t s0 = t0 + (size_t)k * a.sub;
+      const size_t s1 = (s0 + a.sub < t1) ? s0 + a.sub : t1;
+      size_t lo = (size_t)r * a.chunk + s0;
+      size_t cnt = clip_count(lo, (size_t)r * a.chunk + s1, a.n);
+      size_t nv = (cnt + V - 1) / V;
+      char* mc = c.mc_arena + base_off + lo * sizeof(TW);
+      size_t i = t;
+      for (; i + (size_t)(kUnroll - 1) * kPipeRed < nv; i += (size_t)kUnroll * kPipeRed) {
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) v[u] = Multimem<TW>::ld_reduce(mc + (i + (size_t)u * kPipeRed) * 16);
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+          if (a.has_scale) {
+            Pack16<TW> p; p.u = v[u];
+#pragma unroll
+            for (int e = 0; e < V; e++) p.e[e] = Traits<TW>::from_acc(Traits<TW>::to_acc(p.e[e]) * a.scale);
+            v[u] = p.u;
+          }
+          multimem_st16(mc + (i + (size_t)u * kPipeRed) * 16, v[u]);
+        }
+      }
+      for (; i < nv; i += kPipeRed) {
+        uint4 v = Multimem<TW>::ld_reduce(mc + i * 16);
+        if (a.has_scale) {
+          Pack16<TW> p; p.u = v;
+#pragma unroll
+          for (int e = 0; e < V; e++) p.e[e] = Traits<TW>::from_acc(Traits<TW>::to_acc(p.e[e]) * a.scale);
+          v = p.u;
+        }
+        multimem_st16(mc + i * 16, v);
+      }
+      role_sync(2, kPipeRed);
+      if (t < W) st_release_sys(reinterpret_cast<uint32_t*>(c.arena[t] + kOffPipeB) + flag_idx + r, a.pipe_base + k + 1);
+    }
+  } else {
+    // ------------------------------------------------------------------ OUT
+    const int t = tid - kPipeIn - kPipeRed;
+    for (int k = 0; k < K; k++) {
+      if (t < W && !wait_flag(myB + t, a.pipe_base + k + 1, c, t, 2)) s_fail = 1;
+      role_sync(3, kPipeOut);
+      if (s_fail) return;
+      const size_t s0 = t0 + (size_t)k * a.sub;
+      const size_t s1 = (s0 + a.sub < t1) ? s0 + a.sub : t1;
+      for (int j = 0; j < W; j++) {
+        size_t lo = (size_t)j * a.chunk + s0;
+        size_t cnt = clip_count(lo, (size_t)j * a.chunk + s1, a.n);
+        if (cnt) move_tile<TW, TI, true>(out + lo, mine + lo, cnt, t, kPipeOut);
+      }
+    }
+  }
+}
+
 // local elementwise helper for world == 1 (scale / cast only)
 template <typename TI, typename TW>
 __global__ void __launch_bounds__(kThreads) k_local_scale(CollArgs a) {

@@ -30,7 +30,9 @@ constexpr size_t kOffFlagA = 0;                               // u32 [kMaxBlocks
 constexpr size_t kOffFlagB = kOffFlagA + kMaxBlocks * 8 * 4;  // u32 [kMaxBlocks][8]
 constexpr size_t kOffArrive = kOffFlagB + kMaxBlocks * 8 * 4; // u32 [8]   arrive[src] = seq
 constexpr size_t kOffOpSig = kOffArrive + 256;                // u32 [2][8] opsig[seq&1][src] (block 0)
-constexpr size_t kOffP2PReady = kOffOpSig + 256;              // u32 [8 src][kMaxCells]
+constexpr size_t kOffPipeA = kOffOpSig + 256;                 // u32 [kMaxBlocks][8]  pipelined kernels: sub-tile staged in
+constexpr size_t kOffPipeB = kOffPipeA + kMaxBlocks * 8 * 4;  // u32 [kMaxBlocks][8]  pipelined kernels: sub-tile reduced
+constexpr size_t kOffP2PReady = kOffPipeB + kMaxBlocks * 8 * 4;  // u32 [8 src][kMaxCells]
 constexpr int kMaxCells = 1024;
 constexpr size_t kOffP2PAck = kOffP2PReady + 8 * kMaxCells * 4;  // u32 [8 dst][kMaxCells]
 constexpr size_t kPadUsed = kOffP2PAck + 8 * kMaxCells * 4;
@@ -70,6 +72,8 @@ struct CollArgs {
   int root;
   int has_scale;
   float scale;
+  size_t sub;      // pipelined kernels: elements per sub-tile (multiple of the vector width)
+  uint32_t pipe_base;  // pipelined kernels: flag value of sub-tile k is pipe_base + k + 1
   int symmetric;   // NVLS: in/out already live at the same offset of the symmetric region
   size_t sym_off;  // arena offset of that buffer
   const void* in_ptrs[kMaxRanks];
@@ -148,6 +152,11 @@ __device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t seq, co
   for (int i = 0; i < 64; i++)
     if ((int32_t)(ld_acquire_sys(flag) - seq) >= 0) return true;
   return wait_slow(flag, seq, c.status, c.timeout_ns, peer, phase);
+}
+
+// named barrier among `nthreads` (multiple of 32) threads of one warp-specialised role
+__device__ __forceinline__ void role_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // All threads call.  Thread t < world, t != rank waits for flags[t] >= seq.  Returns block-uniform ok.
@@ -276,39 +285,41 @@ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_c
 constexpr int kUnroll = 4;
 
 // Plain byte copy of n elements of T.  SRC_BYPASS: source is staging / peer memory.
+// `t` / `nt`: index of the calling thread within, and size of, the group of threads that cooperates
+// on the tile (the whole CTA by default; one warp-specialised role in the pipelined kernels).
 template <typename T, bool SRC_BYPASS>
-__device__ __forceinline__ void copy_tile(T* __restrict__ dst, const T* __restrict__ src, size_t n) {
+__device__ __forceinline__ void copy_tile(T* __restrict__ dst, const T* __restrict__ src, size_t n,
+                                          int t = threadIdx.x, int nt = kThreads) {
   constexpr int V = 16 / sizeof(T);
-  const int t = threadIdx.x;
   if (aligned16(dst) && aligned16(src)) {
     size_t nv = n / V;
     uint4* d = reinterpret_cast<uint4*>(dst);
     const uint4* s = reinterpret_cast<const uint4*>(src);
     size_t i = t;
-    for (; i + (kUnroll - 1) * kThreads < nv; i += kUnroll * kThreads) {
+    for (; i + (size_t)(kUnroll - 1) * nt < nv; i += (size_t)kUnroll * nt) {
       uint4 v[kUnroll];
 #pragma unroll
-      for (int u = 0; u < kUnroll; u++) v[u] = SRC_BYPASS ? ld_bypass16(s + i + u * kThreads) : s[i + u * kThreads];
+      for (int u = 0; u < kUnroll; u++) v[u] = SRC_BYPASS ? ld_bypass16(s + i + (size_t)u * nt) : s[i + (size_t)u * nt];
 #pragma unroll
-      for (int u = 0; u < kUnroll; u++) d[i + u * kThreads] = v[u];
+      for (int u = 0; u < kUnroll; u++) d[i + (size_t)u * nt] = v[u];
     }
-    for (; i < nv; i += kThreads) d[i] = SRC_BYPASS ? ld_bypass16(s + i) : s[i];
-    for (size_t k = nv * V + t; k < n; k += kThreads) dst[k] = SRC_BYPASS ? ld_bypass(src + k) : src[k];
+    for (; i < nv; i += nt) d[i] = SRC_BYPASS ? ld_bypass16(s + i) : s[i];
+    for (size_t k = nv * V + t; k < n; k += nt) dst[k] = SRC_BYPASS ? ld_bypass(src + k) : src[k];
   } else {
-    for (size_t k = t; k < n; k += kThreads) dst[k] = SRC_BYPASS ? ld_bypass(src + k) : src[k];
+    for (size_t k = t; k < n; k += nt) dst[k] = SRC_BYPASS ? ld_bypass(src + k) : src[k];
   }
 }
 
 // Converting copy TS -> TD through the accumulator domain (fp32 for half types).
 template <typename TS, typename TD, bool SRC_BYPASS>
-__device__ __forceinline__ void convert_tile(TD* __restrict__ dst, const TS* __restrict__ src, size_t n) {
+__device__ __forceinline__ void convert_tile(TD* __restrict__ dst, const TS* __restrict__ src, size_t n,
+                                             int t = threadIdx.x, int nt = kThreads) {
   // vector step = number of elements in 16 bytes of the narrower type
   constexpr int VS = 16 / sizeof(TS), VD = 16 / sizeof(TD);
   constexpr int V = VS > VD ? VS : VD;
-  const int t = threadIdx.x;
   if (aligned16(dst) && aligned16(src)) {
     size_t nv = n / V;
-    for (size_t i = t; i < nv; i += kThreads) {
+    for (size_t i = t; i < nv; i += nt) {
       TS sv[V];
       TD dv[V];
       const uint4* s = reinterpret_cast<const uint4*>(src + i * V);
@@ -330,25 +341,24 @@ __device__ __forceinline__ void convert_tile(TD* __restrict__ dst, const TS* __r
         d[q] = p.u;
       }
     }
-    for (size_t k = nv * V + t; k < n; k += kThreads)
+    for (size_t k = nv * V + t; k < n; k += nt)
       dst[k] = Traits<TD>::from_acc((typename Traits<TD>::A)Traits<TS>::to_acc(SRC_BYPASS ? ld_bypass(src + k) : src[k]));
   } else {
-    for (size_t k = t; k < n; k += kThreads)
+    for (size_t k = t; k < n; k += nt)
       dst[k] = Traits<TD>::from_acc((typename Traits<TD>::A)Traits<TS>::to_acc(SRC_BYPASS ? ld_bypass(src + k) : src[k]));
   }
 }
 
-template <typename TS, typename TD, bool SRC_BYPASS>
-__device__ __forceinline__ void move_tile(TD* dst, const TS* src, size_t n);
-
 template <typename TS, typename TD, bool SRC_BYPASS> struct Mover {
-  static __device__ __forceinline__ void run(TD* dst, const TS* src, size_t n) { convert_tile<TS, TD, SRC_BYPASS>(dst, src, n); }
+  static __device__ __forceinline__ void run(TD* dst, const TS* src, size_t n, int t, int nt) { convert_tile<TS, TD, SRC_BYPASS>(dst, src, n, t, nt); }
 };
 template <typename T, bool SRC_BYPASS> struct Mover<T, T, SRC_BYPASS> {
-  static __device__ __forceinline__ void run(T* dst, const T* src, size_t n) { copy_tile<T, SRC_BYPASS>(dst, src, n); }
+  static __device__ __forceinline__ void run(T* dst, const T* src, size_t n, int t, int nt) { copy_tile<T, SRC_BYPASS>(dst, src, n, t, nt); }
 };
 template <typename TS, typename TD, bool SRC_BYPASS>
-__device__ __forceinline__ void move_tile(TD* dst, const TS* src, size_t n) { Mover<TS, TD, SRC_BYPASS>::run(dst, src, n); }
+__device__ __forceinline__ void move_tile(TD* dst, const TS* src, size_t n, int t = threadIdx.x, int nt = kThreads) {
+  Mover<TS, TD, SRC_BYPASS>::run(dst, src, n, t, nt);
+}
 
 // Reduce `world` sources in rank order into up to two destinations.
 //   src0 + s * src_stride points at rank s's contribution (TW, staging -> bypass loads) except

@@ -1,60 +1,54 @@
 """Backend / ReduceOp / option types of the collective API.
 
-Mirrors ray.util.collective.types (reference python/ray/util/collective/types.py:34-122):
-same names, same defaults, same "options are classes with class attributes" shape, plus the
-`B200` backend constant that selects the peer-memory kernels.  `NCCL` is accepted as an alias
-of `B200` so that actor code written for the reference's default backend runs unchanged.
-The second ReduceOp numbering used by compiled graphs
-(python/ray/experimental/util/types.py:12-17) is `DagReduceOp`.
+API parity with ray.util.collective.types (reference python/ray/util/collective/types.py:34-122):
+the same public names (`Backend`, `ReduceOp`, `AllReduceOptions`, ... `RecvOptions`,
+`unset_timeout_ms`), the same defaults, and option objects that are plain attribute bags.  Added:
+the `B200` backend constant (with `NCCL` kept as an alias so actor code written for the
+reference's default backend runs unchanged) and `DagReduceOp`, the second ReduceOp numbering that
+compiled graphs pass raw to the communicator (python/ray/experimental/util/types.py:12-17).
 """
-from dataclasses import dataclass
+import enum
 from datetime import timedelta
-from enum import Enum
-
-try:
-    import torch as th  # noqa: F401
-
-    _TORCH_AVAILABLE = True
-except ImportError:  # pragma: no cover
-    _TORCH_AVAILABLE = False
-
-try:
-    import cupy as cp  # noqa: F401
-
-    _CUPY_AVAILABLE = True
-except ImportError:
-    _CUPY_AVAILABLE = False
 
 
-def cupy_available():
-    return _CUPY_AVAILABLE
+def _probe(module_name):
+    try:
+        return __import__(module_name)
+    except ImportError:
+        return None
 
 
-def torch_available():
-    return _TORCH_AVAILABLE
+th = _probe("torch")
+cp = _probe("cupy")
+
+
+def torch_available() -> bool:
+    return th is not None
+
+
+def cupy_available() -> bool:
+    return cp is not None
 
 
 class Backend(object):
-    """String-enum of backends; `Backend("nccl")` etc. normalises a user string."""
+    """`Backend("nccl")` normalises a user string to one of the constants below."""
 
     B200 = "B200"
-    NCCL = "B200"  # drop-in: the reference's default backend name selects the B200 kernels
+    NCCL = B200  # drop-in: the reference's default backend name selects the B200 kernels
     GLOO = "GLOO"
     UNRECOGNIZED = "unrecognized"
+    _ALIASES = {"TORCH_GLOO": "GLOO"}
 
     def __new__(cls, name: str):
-        upper_name = name.upper()
-        backend = getattr(Backend, upper_name, Backend.UNRECOGNIZED)
-        if backend == Backend.UNRECOGNIZED:
-            if upper_name == "TORCH_GLOO":
-                return Backend.GLOO
-            raise ValueError(
-                "Unrecognized backend: '{}'. Only B200 (alias NCCL) and GLOO are supported".format(name))
-        return backend
+        key = cls._ALIASES.get(name.upper(), name.upper())
+        value = getattr(Backend, key, Backend.UNRECOGNIZED) if not key.startswith("_") else Backend.UNRECOGNIZED
+        if value == Backend.UNRECOGNIZED:
+            raise ValueError("Unrecognized backend: '{}'. Only B200 (alias NCCL) and GLOO are supported".format(name))
+        return value
 
 
-class ReduceOp(Enum):
-    """ray.util.collective numbering (types.py:55-59)."""
+class ReduceOp(enum.Enum):
+    """ray.util.collective numbering."""
 
     SUM = 0
     PRODUCT = 1
@@ -62,8 +56,8 @@ class ReduceOp(Enum):
     MAX = 3
 
 
-class DagReduceOp(Enum):
-    """ray.experimental.util.types.ReduceOp numbering == ncclRedOp_t (util/types.py:12-17)."""
+class DagReduceOp(enum.Enum):
+    """ray.experimental.util.types.ReduceOp numbering, identical to ncclRedOp_t."""
 
     SUM = 0
     PRODUCT = 1
@@ -75,54 +69,27 @@ class DagReduceOp(Enum):
 unset_timeout_ms = timedelta(milliseconds=-1)
 
 
-@dataclass
-class AllReduceOptions:
-    reduceOp = ReduceOp.SUM
-    timeout_ms = unset_timeout_ms
+def _option_type(name: str, doc: str, **defaults):
+    """An attribute bag with class-level defaults; instances are created empty and callers assign
+    the fields they need, which is how the reference's API layer uses its option dataclasses."""
+    body = dict(defaults)
+    body["__doc__"] = doc
+    body["__repr__"] = lambda self: "{}({})".format(
+        name, ", ".join("{}={!r}".format(k, getattr(self, k)) for k in defaults))
+    return type(name, (object,), body)
 
 
-@dataclass
-class BarrierOptions:
-    timeout_ms = unset_timeout_ms
-
-
-@dataclass
-class ReduceOptions:
-    reduceOp = ReduceOp.SUM
-    root_rank = 0
-    root_tensor = 0
-    timeout_ms = unset_timeout_ms
-
-
-@dataclass
-class AllGatherOptions:
-    timeout_ms = unset_timeout_ms
-
-
-@dataclass
-class BroadcastOptions:
-    root_rank = 0
-    root_tensor = 0
-    timeout_ms = unset_timeout_ms
-
-
-@dataclass
-class ReduceScatterOptions:
-    reduceOp = ReduceOp.SUM
-    timeout_ms = unset_timeout_ms
-
-
-@dataclass
-class SendOptions:
-    dst_rank = 0
-    dst_gpu_index = 0
-    n_elements = 0
-    timeout_ms = unset_timeout_ms
-
-
-@dataclass
-class RecvOptions:
-    src_rank = 0
-    src_gpu_index = 0
-    n_elements = 0
-    unset_timeout_ms = unset_timeout_ms
+AllReduceOptions = _option_type("AllReduceOptions", "allreduce: reduction operator", reduceOp=ReduceOp.SUM,
+                                timeout_ms=unset_timeout_ms)
+BarrierOptions = _option_type("BarrierOptions", "barrier", timeout_ms=unset_timeout_ms)
+ReduceOptions = _option_type("ReduceOptions", "reduce: operator, destination rank (and tensor index)",
+                             reduceOp=ReduceOp.SUM, root_rank=0, root_tensor=0, timeout_ms=unset_timeout_ms)
+AllGatherOptions = _option_type("AllGatherOptions", "allgather", timeout_ms=unset_timeout_ms)
+BroadcastOptions = _option_type("BroadcastOptions", "broadcast: source rank (and tensor index)", root_rank=0,
+                                root_tensor=0, timeout_ms=unset_timeout_ms)
+ReduceScatterOptions = _option_type("ReduceScatterOptions", "reducescatter: reduction operator",
+                                    reduceOp=ReduceOp.SUM, timeout_ms=unset_timeout_ms)
+SendOptions = _option_type("SendOptions", "send: destination rank, optional element-count prefix", dst_rank=0,
+                           dst_gpu_index=0, n_elements=0, timeout_ms=unset_timeout_ms)
+RecvOptions = _option_type("RecvOptions", "recv: source rank, optional element-count prefix", src_rank=0,
+                           src_gpu_index=0, n_elements=0, timeout_ms=unset_timeout_ms)

@@ -61,7 +61,8 @@ typedef enum {
   B200C_ALGO_AUTO = 0,
   B200C_ALGO_ONESHOT = 1, /* every rank pushes its whole buffer to every peer, reduces locally */
   B200C_ALGO_TWOSHOT = 2, /* push reduce-scatter + pull all-gather over peer memory */
-  B200C_ALGO_NVLS = 3     /* multimem.ld_reduce / multimem.st on the NVSwitch multicast object */
+  B200C_ALGO_NVLS = 3,    /* multimem.ld_reduce / multimem.st on the NVSwitch multicast object */
+  B200C_ALGO_NVLS_PIPE = 4 /* same, staged copies overlapped with the switch traffic (warp-specialised pipeline) */
 } b200c_algo_t;
 
 typedef enum {
@@ -92,6 +93,7 @@ typedef struct {
   uint32_t max_blocks;         /* upper bound on CTAs per collective kernel (<= 2048) */
   uint64_t oneshot_max_bytes;  /* AUTO: message <= this -> one-shot */
   uint64_t nvls_min_bytes;     /* AUTO: message >= this and multicast bound -> NVLS */
+  uint64_t nvls_pipe_min_bytes;/* AUTO: staged NVLS pieces >= this use the pipelined kernel (0 = never) */
   uint64_t timeout_ms;         /* device-side bounded spin; 0 = default (30 s) */
 } b200c_config_t;
 

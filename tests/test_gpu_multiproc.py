@@ -255,15 +255,37 @@ def test_nvls_allreduce(raw_world, dtype):
     if not all(get([a.has_multicast.remote() for a in actors])):
         pytest.skip("multicast object not bound on this box")
     for n in (16, 100_003, 3_000_001):
-        for symmetric in (False, True):
+        for symmetric, algo in ((False, N.ALGO_NVLS), (True, N.ALGO_NVLS), (False, N.ALGO_NVLS_PIPE)):
             if symmetric and (n * torch.empty((), dtype=dtype).element_size()) % 16:
                 continue
-            outs = get([a.allreduce.remote(dtype, n, N.SUM, N.ALGO_NVLS, None, symmetric) for a in actors])
+            outs = get([a.allreduce.remote(dtype, n, N.SUM, algo, None, symmetric) for a in actors])
             want = O.allreduce([make_input(dtype, n, r) for r in range(W)])
             tol = 1e-5 if dtype == torch.float32 else (2e-2 if dtype == torch.bfloat16 else 2e-3)
-            assert torch.allclose(outs[0].float(), want.float(), rtol=tol, atol=tol * 4), f"nvls {dtype} n={n} sym={symmetric}"
+            assert torch.allclose(outs[0].float(), want.float(), rtol=tol, atol=tol * 4), f"nvls {dtype} n={n} sym={symmetric} algo={algo}"
             for r in range(1, W):
                 assert_equal_bits(outs[r], outs[0], "every rank must hold identical bits")
+
+
+def test_nvls_pipelined_multi_piece_and_fused(raw_world):
+    """Pipelined staged NVLS: a message of several pieces (staging half is 8 MiB here) and the fused
+    bf16-wire gradient mean; 20 back-to-back launches exercise the sub-tile flag epochs."""
+    from ant_ray_b200 import _native as N
+
+    actors, W = raw_world
+    if not all(get([a.has_multicast.remote() for a in actors])):
+        pytest.skip("multicast object not bound on this box")
+    n = 5_000_011  # 20 MB fp32 -> 3 pieces
+    for _ in range(20):
+        outs = get([a.allreduce.remote(torch.float32, n, N.SUM, N.ALGO_NVLS_PIPE) for a in actors])
+    want = O.allreduce([make_input(torch.float32, n, r) for r in range(W)])
+    assert torch.allclose(outs[0], want, rtol=1e-5, atol=4e-5)
+    for r in range(1, W):
+        assert_equal_bits(outs[r], outs[0], "every rank must hold identical bits")
+    outs = get([a.allreduce.remote(torch.float32, n, N.SUM, N.ALGO_NVLS_PIPE, torch.bfloat16) for a in actors])
+    want = O.allreduce_scaled([make_input(torch.float32, n, r) for r in range(W)], torch.bfloat16, 1.0 / W)
+    assert torch.allclose(outs[0], want, rtol=2e-2, atol=2e-2)
+    for r in range(1, W):
+        assert_equal_bits(outs[r], outs[0], "every rank must hold identical bits")
 
 
 def test_fused_gradient_mean_all_gpus(raw_world):

@@ -62,7 +62,6 @@ def main():
     ap.add_argument("--no-nccl", action="store_true")
     ap.add_argument("--per-iter", action="store_true", help="time every call separately; report min/median/max")
     ap.add_argument("--blocks-list", default="", help="extra communicators with these max_blocks, e.g. 592,1184")
-    ap.add_argument("--hybrid", default="", help="fractions of the message sent through two-shot P2P while NVLS takes the rest, e.g. 0.2,0.3")
     a = ap.parse_args()
     global PER_ITER
     PER_ITER = a.per_iter
@@ -80,12 +79,8 @@ def main():
     extra = {}
     for mb in [int(x) for x in a.blocks_list.split(",") if x]:
         extra[mb] = PeerMemoryComm(world, rank, f"sweep-mb{mb}", local, None, make_config(**{**kw, "max_blocks": mb}))
-    hyb = None
-    if a.hybrid:
-        hyb = (PeerMemoryComm(world, rank, "sweep-hyb-a", local, None, make_config(**kw)),
-               PeerMemoryComm(world, rank, "sweep-hyb-b", local, None, make_config(**kw)),
-               torch.cuda.Stream(), torch.cuda.Stream())
-    algos = {"auto": N.ALGO_AUTO, "oneshot": N.ALGO_ONESHOT, "twoshot": N.ALGO_TWOSHOT, "nvls": N.ALGO_NVLS, "nvls_sym": N.ALGO_NVLS}
+    algos = {"auto": N.ALGO_AUTO, "oneshot": N.ALGO_ONESHOT, "twoshot": N.ALGO_TWOSHOT, "nvls": N.ALGO_NVLS, "nvls_sym": N.ALGO_NVLS,
+             "nvls_pipe": N.ALGO_NVLS_PIPE}
     out = {"world": world, "dtype": a.dtype, "multicast": bool(comm.multicast), "nccl_version": ".".join(map(str, torch.cuda.nccl.version())),
            "max_blocks": comm.config.max_blocks, "rows": []}
     k = 2 * (world - 1) / world
@@ -98,7 +93,7 @@ def main():
             if op == "allreduce":
                 bufs = [torch.ones(n, dtype=dtype, device="cuda") for _ in range(nbuf)]
                 for name in a.algos.split(","):
-                    if name in ("nvls", "nvls_sym") and not comm.multicast:
+                    if name in ("nvls", "nvls_sym", "nvls_pipe") and not comm.multicast:
                         continue
                     if name == "oneshot" and size * world > (a.staging_mb << 20) * 4:
                         continue
@@ -117,22 +112,6 @@ def main():
                             continue
                         us = timeit(lambda b: cx.allreduce(b.data_ptr(), b.data_ptr(), n, nat, N.SUM, algos[name]), bufs, iters, world)
                         row[f"{name}_mb{mb}_us"] = round(us, 2); row[f"{name}_mb{mb}_busbw"] = round(size / us / 1e3 * k, 1)
-                if hyb is not None and comm.multicast and size >= (16 << 20):
-                    ca, cb, sa, sb2 = hyb
-                    for f in [float(x) for x in a.hybrid.split(",")]:
-                        n2 = int(n * f) // 1024 * 1024
-                        n1 = n - n2
-
-                        def both(b):
-                            cur = torch.cuda.current_stream()
-                            sa.wait_stream(cur); sb2.wait_stream(cur)
-                            with torch.cuda.stream(sa):
-                                ca.allreduce(b.data_ptr(), b.data_ptr(), n1, nat, N.SUM, N.ALGO_NVLS)
-                            with torch.cuda.stream(sb2):
-                                cb.allreduce(b.data_ptr() + n1 * esz, b.data_ptr() + n1 * esz, n2, nat, N.SUM, N.ALGO_TWOSHOT)
-                            cur.wait_stream(sa); cur.wait_stream(sb2)
-                        us = timeit(both, bufs, iters, world)
-                        row[f"hybrid{f}_us"] = round(us, 2); row[f"hybrid{f}_busbw"] = round(size / us / 1e3 * k, 1)
                 if not a.no_nccl:
                     us = timeit(lambda b: dist.all_reduce(b), bufs, iters, world)
                     row["nccl_us"] = round(us, 2); row["nccl_busbw"] = round(size / us / 1e3 * k, 1)
@@ -191,8 +170,6 @@ def main():
     comm.check()
     for cx in extra.values():
         cx.check(); cx.destroy()
-    if hyb is not None:
-        hyb[0].destroy(); hyb[1].destroy()
     if rank == 0:
         print(json.dumps(out))
     comm.destroy()
