@@ -688,7 +688,11 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
       if (!sym && algo == B200C_ALGO_AUTO && c->cfg.nvls_pipe_min_bytes && n * wsz >= c->cfg.nvls_pipe_min_bytes) pipe = true;
       if (sym) pipe = false;  // nothing to overlap: the symmetric path has no staging copies
       if (pipe) {
-        a.sub = 8192 / wsz;  // 8 KiB sub-tiles
+        // 16 KiB sub-tiles (two load batches per reduce-role thread) and >= 4 of them per CTA so the
+        // three roles actually overlap; the flag epoch advances by the largest sub-tile count.
+        const size_t sub_bytes = 16384;
+        a.sub = sub_bytes / wsz;
+        plan_tiles(a.chunk, wsz, vec, c->cfg.max_blocks, 4 * sub_bytes, &a.tile, &grid);
         size_t kmax = (a.tile + a.sub - 1) / a.sub;
         a.pipe_base = c->pipe_base;
         c->pipe_base += (uint32_t)kmax;
