@@ -864,9 +864,10 @@ extern "C" int b200c_broadcast(b200c_comm_t* c, void* buf, size_t count, int dty
     base_args(c, &a);
     a.in = static_cast<char*>(buf) + done; a.out = static_cast<char*>(buf) + done;
     a.n = n; a.chunk = round_up(n, 16); a.root = root;
+    a.symmetric = (c->mc_arena && n >= 65536) ? 1 : 0;  // multicast store from the root (same choice on every rank)
     int grid;
     plan_tiles(n, 1, 16, c->cfg.max_blocks, kMinTileBytes, &a.tile, &grid);
-    a.sig = make_sig(OPC_BROADCAST, dtype, 0, n, root, 0);
+    a.sig = make_sig(OPC_BROADCAST, dtype, 0, n, root, a.symmetric);
     k_broadcast<<<grid, kThreads, 0, s>>>(a);
     rc = launch_check("broadcast");
     if (rc) return rc;

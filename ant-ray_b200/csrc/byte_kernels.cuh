@@ -37,6 +37,13 @@ __global__ void __launch_bounds__(kThreads) k_allgather(CollArgs a) {
   }
 }
 
+__device__ __forceinline__ void multimem_st16_bytes(void* p, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// a.symmetric != 0 selects the multicast variant: the root stores each 16-byte vector ONCE to the
+// multicast address of staging slot 0 and the NVSwitch replicates it into every rank's arena
+// (egress S instead of (W-1)*S); the sub-vector tail and unaligned sources go by unicast stores.
 __global__ void __launch_bounds__(kThreads) k_broadcast(CollArgs a) {
   const DevComm& c = a.c;
   const int r = c.rank, W = c.world, root = a.root;
@@ -45,9 +52,28 @@ __global__ void __launch_bounds__(kThreads) k_broadcast(CollArgs a) {
   const size_t cnt = clip_count(t0, t0 + a.tile, a.n);
   if (r == root) {
     if (cnt) {
-      for (int k = 1; k < W; k++) {
-        int j = r + k; if (j >= W) j -= W;
-        copy_tile<uint8_t, false>(staging_ptr<uint8_t>(c, j, a.seq, 0) + t0, static_cast<const uint8_t*>(a.in) + t0, cnt);
+      const uint8_t* src = static_cast<const uint8_t*>(a.in) + t0;
+      size_t done = 0;
+      if (a.symmetric && c.mc_arena && aligned16(src)) {
+        const size_t nv = cnt / 16;
+        const uint4* s = reinterpret_cast<const uint4*>(src);
+        char* mc = c.mc_arena + c.off_staging + (size_t)(a.seq & 1) * c.staging_bytes + t0;
+        size_t i = threadIdx.x;
+        for (; i + (size_t)(kUnroll - 1) * kThreads < nv; i += (size_t)kUnroll * kThreads) {
+          uint4 v[kUnroll];
+#pragma unroll
+          for (int u = 0; u < kUnroll; u++) v[u] = s[i + (size_t)u * kThreads];
+#pragma unroll
+          for (int u = 0; u < kUnroll; u++) multimem_st16_bytes(mc + (i + (size_t)u * kThreads) * 16, v[u]);
+        }
+        for (; i < nv; i += kThreads) multimem_st16_bytes(mc + i * 16, s[i]);
+        done = nv * 16;
+      }
+      if (done < cnt) {
+        for (int k = 1; k < W; k++) {
+          int j = r + k; if (j >= W) j -= W;
+          copy_tile<uint8_t, false>(staging_ptr<uint8_t>(c, j, a.seq, 0) + t0 + done, src + done, cnt - done);
+        }
       }
     }
     block_signal_all(kOffFlagA, a.seq, c);

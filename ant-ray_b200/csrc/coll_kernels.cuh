@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_reducescatter(CollArgs a) {
 template <typename T, int OP>
 __global__ void __launch_bounds__(kThreads, 2) k_reduce(CollArgs a) {
   const DevComm& c = a.c;
-  const int r = c.rank, W = c.world, root = a.root;
+  const int r = c.rank, root = a.root;
   if (!coll_prologue(a)) return;
   const size_t t0 = (size_t)blockIdx.x * a.tile;
   const size_t cnt = clip_count(t0, t0 + a.tile, a.n);

@@ -204,6 +204,16 @@ class RawWorker:
         self.comm.check()
         return x.cpu()
 
+    def broadcast(self, nbytes, root):
+        from ant_ray_b200 import _native as N
+
+        g = torch.Generator().manual_seed(77 + self.rank)
+        x = torch.randint(0, 255, (nbytes,), dtype=torch.uint8, generator=g).cuda()
+        self.comm.broadcast(x.data_ptr(), nbytes, N.UINT8, root)
+        torch.cuda.synchronize()
+        self.comm.check()
+        return x.cpu()
+
     def close(self):
         self.comm.destroy()
         return True
@@ -286,6 +296,18 @@ def test_nvls_pipelined_multi_piece_and_fused(raw_world):
     assert torch.allclose(outs[0], want, rtol=2e-2, atol=2e-2)
     for r in range(1, W):
         assert_equal_bits(outs[r], outs[0], "every rank must hold identical bits")
+
+
+def test_broadcast_all_gpus(raw_world):
+    """Large broadcasts go out as ONE multicast store stream from the root when the multicast object
+    is bound (unicast pushes otherwise); odd byte counts exercise the sub-vector tail."""
+    actors, W = raw_world
+    for root in (0, W - 1):
+        for nbytes in (1000, 100_003, 3_000_000, 20_000_001):  # the last one spans several 8 MiB pieces
+            outs = get([a.broadcast.remote(nbytes, root) for a in actors])
+            want = torch.randint(0, 255, (nbytes,), dtype=torch.uint8, generator=torch.Generator().manual_seed(77 + root))
+            for r in range(W):
+                assert_equal_bits(outs[r], want, f"broadcast {nbytes} B root={root} rank={r}")
 
 
 def test_fused_gradient_mean_all_gpus(raw_world):
