@@ -21,6 +21,9 @@ class B200CollError(RuntimeError):
         super().__init__(message)
         self.status = status
 
+    def __reduce__(self):  # keep (status, message) across process boundaries (Ray / test actors)
+        return (B200CollError, (self.status, self.args[0] if self.args else ""))
+
 
 # b200c_status_t
 OK, EINVAL, ECUDA, ESTATE, EUNSUPPORTED, ETIMEOUT, EABORTED, EMISMATCH, ENOMEM = 0, -1, -2, -3, -4, -5, -6, -7, -8

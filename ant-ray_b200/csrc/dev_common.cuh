@@ -29,7 +29,7 @@ constexpr size_t kPadBytes = 2ull << 20;                      // signal pad = on
 constexpr size_t kOffFlagA = 0;                               // u32 [kMaxBlocks][8]
 constexpr size_t kOffFlagB = kOffFlagA + kMaxBlocks * 8 * 4;  // u32 [kMaxBlocks][8]
 constexpr size_t kOffArrive = kOffFlagB + kMaxBlocks * 8 * 4; // u32 [8]   arrive[src] = seq
-constexpr size_t kOffOpSig = kOffArrive + 256;                // u32 [2][8] opsig[seq&1][src] (block 0)
+constexpr size_t kOffOpSig = kOffArrive + 256;                // u64 [2][8] opsig[seq&1][src] = seq << 32 | signature (block 0)
 constexpr size_t kOffPipeA = kOffOpSig + 256;                 // u32 [kMaxBlocks][8]  pipelined kernels: sub-tile staged in
 constexpr size_t kOffPipeB = kOffPipeA + kMaxBlocks * 8 * 4;  // u32 [kMaxBlocks][8]  pipelined kernels: sub-tile reduced
 constexpr size_t kOffP2PReady = kOffPipeB + kMaxBlocks * 8 * 4;  // u32 [8 src][kMaxCells]
@@ -45,6 +45,7 @@ struct Status {
   volatile unsigned err_seq; // sequence number of the op that failed
   volatile int err_peer;     // peer the kernel was waiting for
   volatile int err_phase;    // 0 = arrive, 1 = flagA, 2 = flagB, 3 = p2p ready, 4 = p2p ack
+  volatile unsigned err_a, err_b;  // mismatch: signature seen / expected
 };
 
 struct DevComm {
@@ -204,8 +205,9 @@ __device__ __forceinline__ bool coll_prologue(const CollArgs& a) {
   const DevComm& c = a.c;
   int t = threadIdx.x;
   if (blockIdx.x == 0 && t < c.world && t != c.rank) {
-    uint32_t* sig = reinterpret_cast<uint32_t*>(c.arena[t] + kOffOpSig) + (a.seq & 1) * 8 + c.rank;
-    st_relaxed_sys(sig, a.sig);
+    unsigned long long* sig = reinterpret_cast<unsigned long long*>(c.arena[t] + kOffOpSig) + (a.seq & 1) * 8 + c.rank;
+    unsigned long long tagged = ((unsigned long long)a.seq << 32) | a.sig;  // one atomic 8-byte store
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(sig), "l"(tagged) : "memory");
     uint32_t* arr = reinterpret_cast<uint32_t*>(c.arena[t] + kOffArrive) + c.rank;
     st_release_sys(arr, a.seq);
   }
@@ -214,18 +216,27 @@ __device__ __forceinline__ bool coll_prologue(const CollArgs& a) {
   if (t < c.world && t != c.rank) ok = wait_flag(arrive + t, a.seq - 1, c, t, 0);
   return __syncthreads_and(ok) != 0;
 }
-// Mismatch detection (block 0 only).  The signature slot is double-buffered by sequence parity and a
-// peer cannot reach op seq+2 before this rank has finished op seq, so once arrive[t] >= seq the
-// slot holds the peer's signature for exactly this op.  On mismatch the communicator is poisoned:
-// the error is recorded and the abort flag raised so this rank's other blocks stop waiting.
+// Mismatch detection (block 0 only, diagnostic).  Each rank announces (seq, signature) to every peer
+// in one atomic 8-byte store.  A peer's announcement is compared only if it carries exactly this
+// op's sequence number; anything else (the peer is still behind, or — a producer-only rank such as
+// a broadcast root — already ahead) is not evidence of a mismatch and is ignored, so the check can
+// never raise a false alarm.  On mismatch the communicator is poisoned: the error is recorded and
+// the abort flag raised so this rank's other blocks stop waiting.
 __device__ __forceinline__ void check_signature(const CollArgs& a) {
   const DevComm& c = a.c;
   int t = threadIdx.x;
   if (blockIdx.x == 0 && t < c.world && t != c.rank) {
     const uint32_t* arrive = reinterpret_cast<const uint32_t*>(c.arena[c.rank] + kOffArrive);
     if (wait_flag(arrive + t, a.seq, c, t, 0)) {
-      uint32_t s = ld_relaxed_sys(reinterpret_cast<const uint32_t*>(c.arena[c.rank] + kOffOpSig) + (a.seq & 1) * 8 + t);
-      if (s != a.sig && s != 0xFFFFFFFFu) { record_error(c.status, B200C_EMISMATCH, a.seq, t, 0); c.status->abort_flag = 1; }  // 0xFFFFFFFF: profiling wildcard
+      const unsigned long long* slot = reinterpret_cast<const unsigned long long*>(c.arena[c.rank] + kOffOpSig) + (a.seq & 1) * 8 + t;
+      unsigned long long v;
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
+      uint32_t s = (uint32_t)v;
+      if ((uint32_t)(v >> 32) == a.seq && s != a.sig) {
+        if (c.status->error == 0) { c.status->err_a = s; c.status->err_b = a.sig; }
+        record_error(c.status, B200C_EMISMATCH, a.seq, t, 0);
+        c.status->abort_flag = 1;
+      }
     }
   }
 }

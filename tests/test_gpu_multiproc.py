@@ -170,9 +170,8 @@ class RawWorker:
         import os
 
         os.environ["B200COLL_STORE"] = f"file://{store_dir}"
+        os.environ["B200COLL_BCAST_MULTICAST"] = "1"  # exercise the multicast broadcast even on a 2-GPU box
         torch.cuda.set_device(rank)
-        from ant_ray_b200.b200_group import PeerMemoryComm, make_config
-
         self.rank, self.world = rank, world
         self.comm = None
 
