@@ -630,7 +630,10 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     if (!has_scale && wire == dtype) { RT(cudaMemcpyAsync(recv, send, count * esz, cudaMemcpyDeviceToDevice, s)); return B200C_OK; }
     CollArgs a; memset(&a, 0, sizeof a);
     a.c = c->dev; a.in = send; a.out = recv; a.n = count; a.has_scale = has_scale; a.scale = scale;
-    int grid; plan_tiles(count, esz, vec, c->cfg.max_blocks * 4 > 1024 ? 1024 : c->cfg.max_blocks * 4, kMinTileBytes, &a.tile, &grid);
+    // no peers to wait for, so the grid is sized for HBM, not for co-residency: up to 8 CTAs per SM,
+    // one CTA per 32 KiB of input
+    size_t want = (count * esz + 32767) / 32768;
+    int grid = (int)(want < 1 ? 1 : (want > (size_t)c->sm_count * 8 ? (size_t)c->sm_count * 8 : want));
     switch (dtype * 16 + wire) {
       case B200C_FLOAT32 * 16 + B200C_FLOAT32: k_local_scale<float, float><<<grid, kThreads, 0, s>>>(a); break;
       case B200C_FLOAT32 * 16 + B200C_BFLOAT16: k_local_scale<float, bf16_t><<<grid, kThreads, 0, s>>>(a); break;

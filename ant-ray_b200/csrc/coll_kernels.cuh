@@ -373,18 +373,50 @@ __global__ void __launch_bounds__(kThreads, 2) k_allreduce_nvls_pipe(CollArgs a)
   }
 }
 
-// local elementwise helper for world == 1 (scale / cast only)
+// world == 1: no peers, only the wire rounding and the scale remain (the DDP hook at N = 1).
+// Grid-stride over 16-byte vectors, four loads in flight per thread; HBM-bound (read n, write n).
+template <typename TI, typename TW>
+__device__ __forceinline__ TI local_scale_one(TI x, const CollArgs& a) {
+  using A = typename Traits<TW>::A;
+  A v = Traits<TW>::to_acc(Traits<TW>::from_acc((A)Traits<TI>::to_acc(x)));
+  if (a.has_scale) v = apply_scale<A>(v, a.scale, 1);
+  return Traits<TI>::from_acc((typename Traits<TI>::A)Traits<TW>::to_acc(Traits<TW>::from_acc(v)));
+}
+
 template <typename TI, typename TW>
 __global__ void __launch_bounds__(kThreads) k_local_scale(CollArgs a) {
-  const size_t t0 = (size_t)blockIdx.x * a.tile;
-  const size_t cnt = clip_count(t0, t0 + a.tile, a.n);
-  const TI* in = static_cast<const TI*>(a.in) + t0;
-  TI* out = static_cast<TI*>(a.out) + t0;
-  using A = typename Traits<TW>::A;
-  for (size_t k = threadIdx.x; k < cnt; k += kThreads) {
-    A v = Traits<TW>::to_acc(Traits<TW>::from_acc((A)Traits<TI>::to_acc(in[k])));
-    if (a.has_scale) v = apply_scale<A>(v, a.scale, 1);
-    out[k] = Traits<TI>::from_acc((typename Traits<TI>::A)Traits<TW>::to_acc(Traits<TW>::from_acc(v)));
+  constexpr int VI = 16 / sizeof(TI);
+  const TI* in = static_cast<const TI*>(a.in);
+  TI* out = static_cast<TI*>(a.out);
+  const size_t n = a.n;
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  const size_t gtid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+  if (aligned16(in) && aligned16(out)) {
+    const size_t nv = n / VI;
+    const uint4* s = reinterpret_cast<const uint4*>(in);
+    uint4* d = reinterpret_cast<uint4*>(out);
+    size_t i = gtid;
+    for (; i + (kUnroll - 1) * stride < nv; i += kUnroll * stride) {
+      Pack16<TI> p[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; u++) p[u].u = s[i + u * stride];
+#pragma unroll
+      for (int u = 0; u < kUnroll; u++) {
+#pragma unroll
+        for (int e = 0; e < VI; e++) p[u].e[e] = local_scale_one<TI, TW>(p[u].e[e], a);
+        d[i + u * stride] = p[u].u;
+      }
+    }
+    for (; i < nv; i += stride) {
+      Pack16<TI> p;
+      p.u = s[i];
+#pragma unroll
+      for (int e = 0; e < VI; e++) p.e[e] = local_scale_one<TI, TW>(p.e[e], a);
+      d[i] = p.u;
+    }
+    for (size_t k = nv * VI + gtid; k < n; k += stride) out[k] = local_scale_one<TI, TW>(in[k], a);
+  } else {
+    for (size_t k = gtid; k < n; k += stride) out[k] = local_scale_one<TI, TW>(in[k], a);
   }
 }
 

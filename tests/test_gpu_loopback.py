@@ -244,3 +244,44 @@ def test_abort_unblocks_a_waiting_kernel():
         assert ei.value.status == N.EABORTED
     finally:
         w.destroy()
+
+
+def test_world_size_one_scale_and_wire_rounding():
+    """W = 1 (the N=1 bench / single-worker TorchTrainer): no peers, only the wire rounding and the
+    scale remain (k_local_scale).  Bit-exact against the oracle, aligned and unaligned, in and out of place."""
+    from ant_ray_b200.b200_group import PeerMemoryComm, make_config
+    from ant_ray_b200.loopback import _MemStore
+
+    comm = PeerMemoryComm(1, 0, "solo", 0, _MemStore(), make_config(staging_bytes=1 << 20))
+    try:
+        for n in (1, 7, 4099, 1_000_003):
+            x = make_input(torch.float32, n + 1, 0)
+            for wire, owire in ((N.BFLOAT16, torch.bfloat16), (N.FLOAT16, torch.float16), (N.FLOAT32, None)):
+                for off in (0, 1):  # off = 1: a view 4 bytes into the allocation -> scalar path
+                    src = x[off:off + n].clone() if off == 0 else x[off:off + n]
+                    d = x.cuda()[off:off + n]
+                    out = torch.empty(n + 1, device="cuda")[off:off + n]
+                    comm.allreduce_scaled(d.data_ptr(), out.data_ptr(), n, N.FLOAT32, wire, 0.25)
+                    torch.cuda.synchronize()
+                    want = O.allreduce_scaled([src], owire, 0.25)
+                    assert_equal_bits(out, want, f"W=1 scaled n={n} wire={wire} off={off}")
+                    comm.allreduce_scaled(d.data_ptr(), d.data_ptr(), n, N.FLOAT32, wire, 0.25)  # in place
+                    torch.cuda.synchronize()
+                    assert_equal_bits(d, want, "in place")
+        h = make_input(torch.bfloat16, 5001, 3)
+        d = h.cuda()
+        comm.allreduce_scaled(d.data_ptr(), d.data_ptr(), 5001, N.BFLOAT16, N.BFLOAT16, 0.5)
+        torch.cuda.synchronize()
+        assert_equal_bits(d, O.allreduce_scaled([h], None, 0.5), "bf16 bucket")
+        # plain ops over one rank: identity / copy
+        a = make_input(torch.int32, 1000, 1).cuda()
+        b = torch.zeros_like(a)
+        comm.allreduce(a.data_ptr(), b.data_ptr(), 1000, N.INT32, N.SUM)
+        comm.allreduce(a.data_ptr(), a.data_ptr(), 1000, N.INT32, N.AVG)
+        comm.broadcast(a.data_ptr(), 1000, N.INT32, 0)
+        comm.barrier()
+        torch.cuda.synchronize()
+        assert_equal_bits(b, a, "W=1 allreduce is a copy")
+        comm.check()
+    finally:
+        comm.destroy()
