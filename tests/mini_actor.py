@@ -34,6 +34,12 @@ def _actor_main(conn, cls, env, args, kwargs):
             return
         call_id, method, a, kw = msg
         try:
+            if method == "__ray_call__":  # run an arbitrary function against the actor instance
+                import cloudpickle
+
+                fn = cloudpickle.loads(a[0])
+                conn.send((call_id, "ok", fn(obj, *a[1:], **kw)))
+                continue
             conn.send((call_id, "ok", getattr(obj, method)(*a, **kw)))
         except BaseException as e:  # noqa: BLE001
             conn.send((call_id, "err", (type(e).__name__, str(e), traceback.format_exc(), _try_pickle(e))))
@@ -59,6 +65,16 @@ class _Method:
         return self.actor._submit(self.name, args, kwargs)
 
 
+class _RayCall:
+    def __init__(self, actor):
+        self.actor = actor
+
+    def remote(self, fn, *args, **kwargs):
+        import cloudpickle
+
+        return self.actor._submit("__ray_call__", (cloudpickle.dumps(fn),) + args, kwargs)
+
+
 class Actor:
     def __init__(self, proc, conn):
         self._proc, self._conn = proc, conn
@@ -66,6 +82,8 @@ class Actor:
         self._done = {}
 
     def __getattr__(self, name):
+        if name == "__ray_call__":
+            return _RayCall(self)
         if name.startswith("_"):
             raise AttributeError(name)
         return _Method(self, name)
