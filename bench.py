@@ -307,6 +307,11 @@ def _cpu_worker(rank, world, port, batch, steps, warmup, threads, q, use_bf16, b
     from torch.nn.parallel import DistributedDataParallel
 
     torch.set_num_threads(threads)
+    # under torchrun the parent's environment tells c10d to join the launcher's agent store as a client;
+    # this private gloo group must bring up its own store instead
+    for k in [k for k in os.environ if k.startswith("TORCHELASTIC_") or k in ("GROUP_RANK", "ROLE_RANK", "LOCAL_RANK", "RANK", "WORLD_SIZE",
+                                                                                   "LOCAL_WORLD_SIZE", "ROLE_WORLD_SIZE", "GROUP_WORLD_SIZE")]:
+        os.environ.pop(k, None)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     device = torch.device("cpu")
@@ -363,6 +368,16 @@ def cpu_reference(world, batch, steps, warmup, budget_s=60.0):
     return world * batch * done / dt, dt / done, threads * world, done, ("bf16 autocast" if use_bf16 else "fp32 (host CPU has no bf16 units)")
 
 
+def workload_config(B, world, wire):
+    """The workload both arms report (the reference arm runs a bounded sample of it)."""
+    return {"workload": "Ray Train TorchTrainer-shaped ResNet-50 DDP step (prepare_model + gradient reduction hook), "
+                        "synthetic randn(B,3,224,224), SGD momentum, bf16 autocast, fp32 grads",
+            "model": "torchvision.resnet50", "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+            "grad_wire": wire, "grad_bytes_per_step": RESNET50_PARAMS * 4,
+            "l2": "per-step working set (activations of 256 images) is far larger than the 126 MB L2; "
+                  "the sweep rotates buffers totalling >= 256 MB"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -375,9 +390,10 @@ def run_reference(args):
         "impl": "reference", "metric": "resnet50_ddp_train_images_per_sec", "value": round(ips, 2), "unit": "images/s",
         "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": round(sps * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "ResNet-50 DDP training step, synthetic 3x224x224 images, SGD, bf16 autocast; reference CPU path "
-                               "(torch DDP over gloo, what ray.train.torch.TorchConfig selects without GPUs)",
-                   "model": "torchvision.resnet50", "per_worker_batch": batch, "global_batch": batch * world, "parallelism": f"dp{world}"},
+        "config": {**workload_config(args.batch, world, args.wire),
+                   "reference_path": "torch DDP default reducer over a gloo process group on the host CPUs (what "
+                                     "ray.train.torch.TorchConfig selects without GPUs, train/torch/config.py:167-176)",
+                   "sample_per_worker_batch": batch},
         "cpu_baseline": {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(ips, 2), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -523,12 +539,7 @@ def main():
             "metric": "resnet50_ddp_train_images_per_sec", "value": round(value, 1), "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "Ray Train TorchTrainer-shaped ResNet-50 DDP step (prepare_model + fused B200 gradient hook), "
-                                   "synthetic randn(B,3,224,224), SGD momentum, bf16 autocast, fp32 grads",
-                       "model": "torchvision.resnet50", "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "grad_wire": args.wire, "grad_bytes_per_step": RESNET50_PARAMS * 4,
-                       "l2": "per-step working set (activations of 256 images) is far larger than the 126 MB L2; "
-                             "the sweep rotates buffers totalling >= 256 MB"},
+            "config": workload_config(B, world, args.wire),
             "clocks": sampler.summary([win1, win2]) if sampler else None,
             "e2e": {"value": round(e2e, 1), "unit": "images/s", "h2d_bytes_per_step": x_host_cl.numel() * 4 + y_host.numel() * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last_loss},
