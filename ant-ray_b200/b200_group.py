@@ -190,9 +190,6 @@ class PeerMemoryComm:
             self._last_stream = cur
         return cur
 
-    def after_launch(self, stream):
-        pass
-
     def check(self):
         N.check(self.lib.b200c_comm_check(self.handle))
 
@@ -238,52 +235,43 @@ class PeerMemoryComm:
     def allreduce(self, send_ptr, recv_ptr, count, dtype, op, algo=N.ALGO_AUTO):
         s = self.stream()
         N.check(self.lib.b200c_allreduce(self._h(), send_ptr, recv_ptr, count, dtype, op, algo, s.cuda_stream))
-        self.after_launch(s)
 
     def allreduce_scaled(self, send_ptr, recv_ptr, count, dtype, wire_dtype, scale, algo=N.ALGO_AUTO):
         s = self.stream()
         N.check(self.lib.b200c_allreduce_scaled(self._h(), send_ptr, recv_ptr, count, dtype, wire_dtype, scale, algo,
                                                 s.cuda_stream))
-        self.after_launch(s)
 
     def reduce(self, send_ptr, recv_ptr, count, dtype, op, root):
         s = self.stream()
         N.check(self.lib.b200c_reduce(self._h(), send_ptr, recv_ptr, count, dtype, op, root, s.cuda_stream))
-        self.after_launch(s)
 
     def broadcast(self, ptr, count, dtype, root):
         s = self.stream()
         N.check(self.lib.b200c_broadcast(self._h(), ptr, count, dtype, root, s.cuda_stream))
-        self.after_launch(s)
 
     def allgather(self, send_ptr, recv_ptrs: List[int], count, dtype):
         s = self.stream()
         arr = (ctypes.c_void_p * len(recv_ptrs))(*recv_ptrs)
         N.check(self.lib.b200c_allgather(self._h(), send_ptr, arr, count, dtype, s.cuda_stream))
-        self.after_launch(s)
 
     def reducescatter(self, send_ptrs: List[int], recv_ptr, count, dtype, op):
         s = self.stream()
         arr = (ctypes.c_void_p * len(send_ptrs))(*send_ptrs)
         N.check(self.lib.b200c_reducescatter(self._h(), arr, recv_ptr, count, dtype, op, s.cuda_stream))
-        self.after_launch(s)
 
     def send(self, ptr, nbytes, peer, stream=None):
         s = self.stream() if stream is None else stream
         N.check(self.lib.b200c_send(self._h(), ptr, nbytes, peer, s.cuda_stream))
         if stream is None:
-            self.after_launch(s)
-
+    
     def recv(self, ptr, nbytes, peer, stream=None):
         s = self.stream() if stream is None else stream
         N.check(self.lib.b200c_recv(self._h(), ptr, nbytes, peer, s.cuda_stream))
         if stream is None:
-            self.after_launch(s)
-
+    
     def barrier(self):
         s = self.stream()
         N.check(self.lib.b200c_barrier(self._h(), s.cuda_stream))
-        self.after_launch(s)
         return s
 
 

@@ -19,7 +19,7 @@ Register it with `register_accelerator_context("cuda", B200Communicator)`
 """
 import uuid
 from abc import ABC, abstractmethod
-from typing import Callable, List, Optional, Tuple
+from typing import Callable, Optional, Tuple
 
 from . import _native as N
 from .b200_group import PeerMemoryComm, TensorView, native_reduce_op

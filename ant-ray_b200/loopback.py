@@ -12,7 +12,6 @@ from typing import List, Optional
 
 import torch
 
-from . import _native as N
 from . import rendezvous
 from .b200_group import PeerMemoryComm, make_config
 

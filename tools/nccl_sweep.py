@@ -6,7 +6,6 @@ cupy is absent in this image so the same NCCL entry point is reached via torch c
 """
 import json
 import os
-import sys
 
 import torch
 import torch.distributed as dist
