@@ -262,13 +262,11 @@ class PeerMemoryComm:
     def send(self, ptr, nbytes, peer, stream=None):
         s = self.stream() if stream is None else stream
         N.check(self.lib.b200c_send(self._h(), ptr, nbytes, peer, s.cuda_stream))
-        if stream is None:
-    
+
     def recv(self, ptr, nbytes, peer, stream=None):
         s = self.stream() if stream is None else stream
         N.check(self.lib.b200c_recv(self._h(), ptr, nbytes, peer, s.cuda_stream))
-        if stream is None:
-    
+
     def barrier(self):
         s = self.stream()
         N.check(self.lib.b200c_barrier(self._h(), s.cuda_stream))
