@@ -11,7 +11,7 @@ def test_every_module_imports():
     assert {"collective", "b200_group", "communicator", "channel", "ddp_hook", "train", "rendezvous", "loopback", "_native",
             "types", "experimental_collective", "rdt_transport"} <= set(names)
     for n in names:
-        if n == "_ray_actors":  # needs a Ray installation
+        if n == "_ray_actors" or n.startswith("lib"):  # needs Ray / is the native library, not a Python module
             continue
         importlib.import_module(f"ant_ray_b200.{n}")
 
