@@ -75,11 +75,37 @@ class _RayCall:
         return self.actor._submit("__ray_call__", (cloudpickle.dumps(fn),) + args, kwargs)
 
 
+class ActorId:
+    """What travels when an actor handle is pickled into another actor (identity only)."""
+
+    def __init__(self, uid):
+        self._ray_actor_id = uid
+
+    def __eq__(self, other):
+        return getattr(other, "_ray_actor_id", None) == self._ray_actor_id
+
+    def __hash__(self):
+        return hash(self._ray_actor_id)
+
+
 class Actor:
+    _counter = 0
+
     def __init__(self, proc, conn):
         self._proc, self._conn = proc, conn
         self._next = 0
         self._done = {}
+        Actor._counter += 1
+        self._ray_actor_id = f"actor-{os.getpid()}-{Actor._counter}"
+
+    def __reduce__(self):
+        return (ActorId, (self._ray_actor_id,))
+
+    def __eq__(self, other):
+        return getattr(other, "_ray_actor_id", None) == self._ray_actor_id
+
+    def __hash__(self):
+        return hash(self._ray_actor_id)
 
     def __getattr__(self, name):
         if name == "__ray_call__":

@@ -9,7 +9,7 @@ import ant_ray_b200
 def test_every_module_imports():
     names = [m.name for m in pkgutil.iter_modules(ant_ray_b200.__path__)]
     assert {"collective", "b200_group", "communicator", "channel", "ddp_hook", "train", "rendezvous", "loopback", "_native",
-            "types", "experimental_collective", "rdt_transport", "collective_op"} <= set(names)
+            "types", "experimental_collective", "rdt_transport", "collective_op", "channel_context"} <= set(names)
     for n in names:
         if n == "_ray_actors" or n.startswith("lib"):  # needs Ray / is the native library, not a Python module
             continue
