@@ -465,20 +465,24 @@ def main():
     # ---- stock DDP reducer over NCCL on the same box (B-DDP baseline)
     nccl_ddp = None
     log("stock NCCL DDP baseline")
+    optional_errors = {}
     if not args.no_nccl_ddp:
-        from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
-        from torch.nn.parallel import DistributedDataParallel
+        try:  # a failure of an optional section must not cost the headline line
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+            from torch.nn.parallel import DistributedDataParallel
 
-        m2 = DistributedDataParallel(build_model(device), device_ids=[device], output_device=device)
-        if args.wire == "bf16":
-            m2.register_comm_hook(None, default_hooks.bf16_compress_hook)
-        o2 = torch.optim.SGD(m2.parameters(), lr=0.01, momentum=0.9)
-        s2 = make_step(m2, o2, use_autocast=True, device=device)
-        for _ in range(max(3, args.warmup)):
-            s2(x, y)
-        ms2, _, _ = timed_steps(s2, x, y, args.steps, dist, world)
-        nccl_ddp = world * B * args.steps / (ms2 / 1e3)
-        del m2, o2, s2
+            m2 = DistributedDataParallel(build_model(device), device_ids=[device], output_device=device)
+            if args.wire == "bf16":
+                m2.register_comm_hook(None, default_hooks.bf16_compress_hook)
+            o2 = torch.optim.SGD(m2.parameters(), lr=0.01, momentum=0.9)
+            s2 = make_step(m2, o2, use_autocast=True, device=device)
+            for _ in range(max(3, args.warmup)):
+                s2(x, y)
+            ms2, _, _ = timed_steps(s2, x, y, args.steps, dist, world)
+            nccl_ddp = world * B * args.steps / (ms2 / 1e3)
+            del m2, o2, s2
+        except Exception as e:  # noqa: BLE001
+            optional_errors["nccl_ddp"] = repr(e)[:300]
 
     # ---- allreduce sweep
     sweep = None
@@ -486,14 +490,17 @@ def main():
     if not args.no_sweep:
         del model, opt, step
         torch.cuda.empty_cache()
-        if world > 1:
-            from ant_ray_b200.b200_group import PeerMemoryComm, next_comm_key
+        try:
+            if world > 1:
+                from ant_ray_b200.b200_group import PeerMemoryComm, next_comm_key
 
-            sweep_comm = PeerMemoryComm(world, rank, next_comm_key("bench-sweep"), local)  # default (full-size) grid
-            sweep = run_sweep_multi(sweep_comm, dist, world, args.sweep_max_bytes)
-            sweep_comm.destroy()
-        elif rank == 0:
-            sweep = run_sweep_loopback(args.sweep_max_bytes)
+                sweep_comm = PeerMemoryComm(world, rank, next_comm_key("bench-sweep"), local)  # default (full-size) grid
+                sweep = run_sweep_multi(sweep_comm, dist, world, args.sweep_max_bytes)
+                sweep_comm.destroy()
+            elif rank == 0:
+                sweep = run_sweep_loopback(args.sweep_max_bytes)
+        except Exception as e:  # noqa: BLE001
+            optional_errors["allreduce_sweep"] = repr(e)[:300]
 
     if sampler is not None:
         sampler.stop()
@@ -531,9 +538,12 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cb = int(os.environ.get("BENCH_CPU_BATCH", 16))
             log("cpu baseline (bounded sample) ...")
-            ips, sps, cores, done, cpu_dtype = cpu_reference(1, cb, 3, 1, budget_s=float(os.environ.get("BENCH_CPU_BUDGET_S", 45)))
-            cpu_baseline = {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": "port",
-                            "sample": f"1 gloo worker x batch {cb}, {done} steps after 1 warm-up (torch DDP default reducer, {cpu_dtype}, host CPU)"}
+            try:
+                ips, sps, cores, done, cpu_dtype = cpu_reference(1, cb, 3, 1, budget_s=float(os.environ.get("BENCH_CPU_BUDGET_S", 45)))
+                cpu_baseline = {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": f"1 gloo worker x batch {cb}, {done} steps after 1 warm-up (torch DDP default reducer, {cpu_dtype}, host CPU)"}
+            except Exception as e:  # noqa: BLE001
+                optional_errors["cpu_baseline"] = repr(e)[:300]
         hook_total = sum(t for t, _ in ktimes) / max(1, args.steps)
         out = {
             "metric": "resnet50_ddp_train_images_per_sec", "value": round(value, 1), "unit": "images/s", "n_gpus": world,
@@ -552,6 +562,8 @@ def main():
             "multicast": bool(state.comm.multicast),
             "allreduce_sweep": sweep,
         }
+        if optional_errors:
+            out["optional_section_errors"] = optional_errors
         print(json.dumps(out))
     state.comm.destroy()
     dist.destroy_process_group()
