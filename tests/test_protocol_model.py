@@ -1,0 +1,216 @@
+"""Randomised model check of the peer-memory flag protocol (csrc/dev_common.cuh, coll_kernels.cuh).
+
+The reference documents its races instead of detecting them ("TODO: we need a lock here",
+nccl_collective_group.py:127,400,415).  The new layer's main risk is the
+flag protocol, so this test executes a faithful model of it under random interleavings and
+asserts the two safety properties the kernels rely on:
+
+  S1  a staging region is never overwritten while a rank that still has to read its previous
+      content has not read it (double buffering by sequence parity + the `arrive` rule of
+      coll_prologue());
+  S2  every read observes the content written for exactly the reader's own op.
+
+Modelled: W ranks, B blocks per kernel, kernels of one rank strictly ordered (one stream), blocks of
+a kernel in arbitrary order, cross-rank flags monotonically increasing, ops = two-shot allreduce,
+one-shot allreduce, staged NVLS allreduce, broadcast (root runs ahead without waiting for anyone), reduce (non-roots wait
+for the root's release), barrier.  Each rank's block executes the same step list the CUDA code
+does.  The last test removes the `arrive` wait and shows that the checker then finds a violation —
+i.e. the rule is necessary and the model can see that.
+"""
+import random
+
+import pytest
+
+
+class Violation(AssertionError):
+    pass
+
+
+class World:
+    def __init__(self, W, B, ops, use_arrive_rule=True):
+        self.W, self.B, self.ops, self.rule = W, B, ops, use_arrive_rule
+        self.arrive = [[0] * W for _ in range(W)]                       # arrive[rank][src]
+        self.flagA = [[[0] * W for _ in range(B)] for _ in range(W)]    # flagA[rank][block][src]
+        self.flagB = [[[0] * W for _ in range(B)] for _ in range(W)]
+        self.content = {}     # region -> seq of the data it holds
+        self.pending = {}     # region -> set of (rank, block) that still have to read that data
+        self.op_idx = [0] * W                                            # kernel each rank is in
+        self.pc = [[0] * B for _ in range(W)]                            # step index of each block
+        self.steps = [[self._program(r, b, 0) for b in range(B)] for r in range(W)]
+
+    # ---- what the kernels do, as step lists ---------------------------------------------------
+    def _program(self, r, b, k):
+        if k >= len(self.ops):
+            return []
+        kind, root = self.ops[k]
+        q, W, h = k + 1, self.W, (k + 1) & 1
+        peers = [j for j in range(W) if j != r]
+        st = []
+        if kind == "barrier":
+            if b == 0:
+                st += [("set_arrive", j, q) for j in peers] + [("wait_arrive", j, q) for j in peers]
+            return st
+        # coll_prologue: block 0 publishes arrive = q; every block waits arrive >= q-1 from every peer
+        if b == 0:
+            st += [("set_arrive", j, q) for j in peers]
+        if self.rule:
+            st += [("wait_arrive", j, q - 1) for j in peers]
+        if kind == "twoshot":
+            st += [("write", (j, h, r, b), q, {(j, b)}) for j in peers]                      # A: push chunk j to rank j's slot r
+            st += [("sigA", j, q) for j in peers] + [("waitA", j, q) for j in peers]
+            st += [("read", (r, h, s, b), q) for s in peers]                                 # B: fold the W contributions
+            st += [("write", (r, h, r, b), q, {(j, b) for j in peers})]                      #    result -> own slot (peers pull it)
+            st += [("sigB", j, q) for j in peers] + [("waitB", j, q) for j in peers]
+            st += [("read", (j, h, j, b), q) for j in peers]                                 # C: pull the reduced chunks
+        elif kind == "oneshot":
+            st += [("write", (j, h, r, b), q, {(j, b)}) for j in peers]
+            st += [("sigA", j, q) for j in peers] + [("waitA", j, q) for j in peers]
+            st += [("read", (r, h, s, b), q) for s in peers]
+        elif kind == "nvls":
+            everyone = list(range(W))
+            st += [("write", (r, h, "in", b), q, {(j, b) for j in everyone})]                # A: stage in (own arena)
+            st += [("sigA", j, q) for j in peers] + [("waitA", j, q) for j in peers]
+            st += [("read", (j, h, "in", b), q) for j in everyone]                           # B: the switch reads every rank's copy
+            st += [("write", (j, h, ("out", r), b), q, {(j, b)}) for j in everyone]          #    ... and multicasts the result back
+            st += [("sigB", j, q) for j in peers] + [("waitB", j, q) for j in peers]
+            st += [("read", (r, h, ("out", j), b), q) for j in everyone]                     # C: stage out
+        elif kind == "broadcast":
+            if r == root:
+                st += [("write", (j, h, 0, b), q, {(j, b)}) for j in peers]                  # root pushes, waits for nobody
+                st += [("sigA", j, q) for j in peers]
+            else:
+                st += [("waitA", root, q), ("read", (r, h, 0, b), q)]
+        elif kind == "reduce":
+            if r != root:
+                st += [("write", (root, h, r, b), q, {(root, b)}), ("sigA", root, q), ("waitB", root, q)]
+            else:
+                st += [("waitA", j, q) for j in peers] + [("read", (r, h, s, b), q) for s in peers]
+                st += [("sigB", j, q) for j in peers]
+        else:
+            raise ValueError(kind)
+        return st
+
+    # ---- execution ----------------------------------------------------------------------------
+    def runnable(self):
+        out = []
+        for r in range(self.W):
+            for b in range(self.B):
+                if self.pc[r][b] < len(self.steps[r][b]) and self._ready(r, b, self.steps[r][b][self.pc[r][b]]):
+                    out.append((r, b))
+        return out
+
+    def _ready(self, r, b, step):
+        op = step[0]
+        if op == "wait_arrive":
+            return self.arrive[r][step[1]] >= step[2]
+        if op == "waitA":
+            return self.flagA[r][b][step[1]] >= step[2]
+        if op == "waitB":
+            return self.flagB[r][b][step[1]] >= step[2]
+        return True
+
+    def step(self, r, b):
+        s = self.steps[r][b][self.pc[r][b]]
+        op = s[0]
+        if op == "set_arrive":
+            self.arrive[s[1]][r] = max(self.arrive[s[1]][r], s[2])
+        elif op == "sigA":
+            self.flagA[s[1]][b][r] = s[2]
+        elif op == "sigB":
+            self.flagB[s[1]][b][r] = s[2]
+        elif op == "write":
+            region, q, readers = s[1], s[2], s[3]
+            # Conservative aliasing: one-shot and two-shot lay slots and tiles out differently inside a
+            # half, so a write may land on ANY older data of the same (rank, half).  Data of the same op
+            # is disjoint by construction (distinct slot / tile per writer).
+            for other, seq in self.content.items():
+                if other[:2] == region[:2] and seq != q and self.pending.get(other):
+                    raise Violation(f"S1: rank {r} block {b} op {q} writes {region} while {sorted(self.pending[other])} "
+                                    f"still have to read op {seq} data in {other} of the same staging half")
+            self.content[region], self.pending[region] = q, set(readers)
+        elif op == "read":
+            region, q = s[1], s[2]
+            if self.content.get(region) != q:
+                raise Violation(f"S2: rank {r} block {b} op {q} reads {region} holding op {self.content.get(region)}")
+            self.pending[region].discard((r, b))
+        self.pc[r][b] += 1
+        # kernel boundary: the next kernel of this rank starts only when every block of this one is done
+        if all(self.pc[r][x] >= len(self.steps[r][x]) for x in range(self.B)) and self.op_idx[r] < len(self.ops):
+            self.op_idx[r] += 1
+            for x in range(self.B):
+                self.steps[r][x] = self._program(r, x, self.op_idx[r])
+                self.pc[r][x] = 0
+
+    def run(self, rng, bias=None):
+        """Random scheduler; `bias(r, b)` may weight the choice (e.g. make one rank slow)."""
+        n = 0
+        while True:
+            if all(self.op_idx[r] >= len(self.ops) for r in range(self.W)):
+                return n
+            cands = self.runnable()
+            if not cands:
+                raise Violation(f"deadlock: op_idx={self.op_idx}")
+            if bias is not None:
+                weights = [bias(r, b) for r, b in cands]
+                r, b = rng.choices(cands, weights=weights)[0]
+            else:
+                r, b = rng.choice(cands)
+            self.step(r, b)
+            n += 1
+
+
+def random_ops(rng, W, n):
+    kinds = ["twoshot", "oneshot", "nvls", "broadcast", "reduce", "barrier"]
+    return [(k, rng.randrange(W)) for k in (rng.choice(kinds) for _ in range(n))]
+
+
+@pytest.mark.parametrize("W,B", [(2, 1), (2, 3), (3, 2), (4, 2), (8, 1)])
+def test_protocol_is_safe_under_random_interleavings(W, B):
+    rng = random.Random(1000 * W + B)
+    total = 0
+    for trial in range(60):
+        ops = random_ops(rng, W, 12)
+        slow = rng.randrange(W)
+        bias = [None, lambda r, b: 0.05 if r == slow else 1.0, lambda r, b: 20.0 if r == slow else 1.0][trial % 3]
+        total += World(W, B, ops).run(rng, bias)
+    assert total > 0
+
+
+def test_broadcast_root_runs_ahead_but_never_two_ops():
+    """A producer-only root may be one op ahead of a slow reader (other staging half), never two."""
+    rng = random.Random(7)
+    ops = [("broadcast", 0)] * 10
+    for _ in range(50):
+        w = World(3, 2, ops)
+        lead = 0
+        while not all(i >= len(ops) for i in w.op_idx):
+            cands = w.runnable()
+            # starve rank 2: it only runs when nothing else can
+            pick = [c for c in cands if c[0] != 2] or cands
+            w.step(*rng.choice(pick))
+            lead = max(lead, w.op_idx[0] - w.op_idx[2])
+        assert 1 <= lead <= 2  # "2" = root has *entered* kernel q+2's prologue and is parked on arrive
+
+
+def test_checker_has_teeth_without_the_arrive_rule():
+    """Drop the prologue wait: a run-ahead broadcast root overwrites a staging half a slow reader has
+    not read yet.  The model must catch it, otherwise the test above proves nothing."""
+    rng = random.Random(3)
+    ops = [("broadcast", 0)] * 6
+    caught = 0
+    for _ in range(40):
+        try:
+            World(3, 1, ops, use_arrive_rule=False).run(rng, lambda r, b: 50.0 if r == 0 else 1.0)
+        except Violation as e:
+            assert str(e).startswith(("S1", "S2"))
+            caught += 1
+    assert caught > 0
+
+
+def test_mixed_algorithms_share_the_staging_safely():
+    """one-shot and two-shot lay their slots out differently inside the same half; alternate them with
+    asymmetric ops in between and with one rank much slower than the others."""
+    rng = random.Random(11)
+    ops = [("twoshot", 0), ("broadcast", 1), ("oneshot", 0), ("reduce", 2), ("twoshot", 0), ("broadcast", 0), ("oneshot", 0)] * 3
+    for slow in range(4):
+        World(4, 2, ops).run(rng, lambda r, b: 0.02 if r == slow else 1.0)
