@@ -214,3 +214,68 @@ def test_mixed_algorithms_share_the_staging_safely():
     ops = [("twoshot", 0), ("broadcast", 1), ("oneshot", 0), ("reduce", 2), ("twoshot", 0), ("broadcast", 0), ("oneshot", 0)] * 3
     for slow in range(4):
         World(4, 2, ops).run(rng, lambda r, b: 0.02 if r == slow else 1.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# p2p ring (k_send / k_recv): cell k of a pair's lifetime lives at ring position k % CELLS and
+# carries flag value k+1; the sender may reuse a position only after the receiver acked its
+# previous occupant.  Blocks of a kernel take cells i, i+grid, ...
+# ---------------------------------------------------------------------------------------------
+def _run_ring(rng, cells, messages, send_grid, recv_grid, recv_bias):
+    ready, ack, ring = [0] * cells, [0] * cells, [None] * cells
+    unread = [False] * cells
+    # build per-block work lists for the whole message sequence, kernel by kernel
+    def kernels(grid):
+        out, first = [], 0
+        for n in messages:
+            g = min(n, grid, cells)
+            out.append([[first + i for i in range(b, n, g)] for b in range(g)])
+            first += n
+        return out
+    S, R = kernels(send_grid), kernels(recv_grid)
+    si = ri = 0
+    spc, rpc = [0] * len(S[0]), [0] * len(R[0])
+    got = []
+    while si < len(S) or ri < len(R):
+        cands = []
+        if si < len(S):
+            for b, lst in enumerate(S[si]):
+                if spc[b] < len(lst):
+                    k = lst[spc[b]]
+                    if k < cells or ack[k % cells] >= k + 1 - cells:
+                        cands.append(("s", b))
+        if ri < len(R):
+            for b, lst in enumerate(R[ri]):
+                if rpc[b] < len(lst) and ready[lst[rpc[b]] % cells] >= lst[rpc[b]] + 1:
+                    cands.append(("r", b))
+        assert cands, "p2p ring deadlock"
+        side, b = rng.choices(cands, weights=[recv_bias if c[0] == "r" else 1.0 for c in cands])[0]
+        if side == "s":
+            k = S[si][b][spc[b]]
+            pos = k % cells
+            assert not unread[pos], f"cell {k} overwrites ring position {pos} before it was consumed"
+            ring[pos], unread[pos], ready[pos] = k, True, k + 1
+            spc[b] += 1
+            if all(spc[x] >= len(S[si][x]) for x in range(len(S[si]))):
+                si += 1
+                spc = [0] * len(S[si]) if si < len(S) else []
+        else:
+            k = R[ri][b][rpc[b]]
+            pos = k % cells
+            assert ring[pos] == k, f"receiver expected cell {k} at position {pos}, found {ring[pos]}"
+            got.append(k)
+            unread[pos], ack[pos] = False, k + 1
+            rpc[b] += 1
+            if all(rpc[x] >= len(R[ri][x]) for x in range(len(R[ri]))):
+                ri += 1
+                rpc = [0] * len(R[ri]) if ri < len(R) else []
+    assert sorted(got) == list(range(sum(messages)))
+
+
+@pytest.mark.parametrize("cells", [4, 16])
+def test_p2p_ring_flow_control(cells):
+    rng = random.Random(cells)
+    for trial in range(200):
+        messages = [rng.randint(1, 3 * cells) for _ in range(rng.randint(1, 6))]
+        _run_ring(rng, cells, messages, send_grid=rng.randint(1, cells), recv_grid=rng.randint(1, cells),
+                  recv_bias=[0.05, 1.0, 20.0][trial % 3])
