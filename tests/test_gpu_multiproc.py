@@ -213,6 +213,30 @@ class RawWorker:
         self.comm.check()
         return x.cpu()
 
+    def big_properties(self, n):
+        """Size-independent checks at BASELINE's largest message (1 GiB): see test_full_size_properties."""
+        from ant_ray_b200 import _native as N
+
+        g = torch.Generator(device="cuda").manual_seed(4321 + self.rank)
+        x = torch.randint(-2**31, 2**31 - 1, (n,), dtype=torch.int32, device="cuda", generator=g)
+        local = int(x.sum(dtype=torch.int64).item())
+        self.comm.allreduce(x.data_ptr(), x.data_ptr(), n, N.INT32, N.SUM)
+        torch.cuda.synchronize()
+        self.comm.check()
+        total = int(x.sum(dtype=torch.int64).item())
+        edges = torch.cat([x[:4], x[n // 2:n // 2 + 4], x[-4:]]).cpu()
+        y = x.clone()
+        self.comm.allreduce(y.data_ptr(), y.data_ptr(), n, N.INT32, N.MAX)  # MAX of identical buffers: idempotent
+        torch.cuda.synchronize()
+        idempotent = bool(torch.equal(x, y))
+        del y
+        f = torch.full((n,), 1.0, dtype=torch.float32, device="cuda")      # the reference's known-answer fill, full size
+        self.comm.allreduce(f.data_ptr(), f.data_ptr(), n, N.FLOAT32, N.SUM)
+        torch.cuda.synchronize()
+        self.comm.check()
+        fill_ok = bool((f == float(self.world)).all().item())
+        return local, total, idempotent, fill_ok, edges
+
     def close(self):
         self.comm.destroy()
         return True
@@ -307,6 +331,27 @@ def test_broadcast_all_gpus(raw_world):
             want = torch.randint(0, 255, (nbytes,), dtype=torch.uint8, generator=torch.Generator().manual_seed(77 + root))
             for r in range(W):
                 assert_equal_bits(outs[r], want, f"broadcast {nbytes} B root={root} rank={r}")
+
+
+def test_full_size_properties(raw_world):
+    """BASELINE.json's largest message (1 GiB, 2^28 elements) is too big to check element by element
+    against the CPU oracle in seconds, so it is checked through size-independent properties:
+      * int32 SUM wraps modulo 2^32, hence  sum_i result[i] == sum_r sum_i x_r[i]  (mod 2^32)
+        -- a checksum of checksums computed on the GPUs in int64;
+      * every rank ends with identical bits (same checksum, same sampled elements);
+      * MAX over already-identical buffers is idempotent;
+      * a constant fill of ones sums to exactly W (the reference's known-answer test at full size).
+    The message spans >100 staging pieces here (8 MiB staging), so piece boundaries are covered too."""
+    actors, W = raw_world
+    n = 1 << 28
+    res = get([a.big_properties.remote(n) for a in actors], timeout=600)
+    locals_, totals = [r[0] for r in res], [r[1] for r in res]
+    assert len(set(totals)) == 1, "ranks disagree on the checksum of the result"
+    assert (sum(locals_) - totals[0]) % (1 << 32) == 0, "checksum of checksums mismatch"
+    for r in range(W):
+        assert res[r][2], f"rank {r}: MAX was not idempotent"
+        assert res[r][3], f"rank {r}: fill of ones did not sum to W everywhere"
+        assert torch.equal(res[r][4], res[0][4])
 
 
 def test_fused_gradient_mean_all_gpus(raw_world):
