@@ -285,3 +285,34 @@ def test_world_size_one_scale_and_wire_rounding():
         comm.check()
     finally:
         comm.destroy()
+
+
+def test_full_size_properties_loopback():
+    """256 MiB per rank (many staging pieces) checked through size-independent properties, as in
+    test_gpu_multiproc.py::test_full_size_properties, but runnable on a single GPU."""
+    from ant_ray_b200.loopback import LoopbackWorld
+
+    W, n = 2, 1 << 26
+    w = LoopbackWorld(W, device=0, key="lb-big", staging_bytes=32 << 20, timeout_ms=30000)
+    try:
+        xs = [torch.randint(-2**31, 2**31 - 1, (n,), dtype=torch.int32, device="cuda",
+                            generator=torch.Generator(device="cuda").manual_seed(99 + r)) for r in range(W)]
+        locals_ = [int(x.sum(dtype=torch.int64).item()) for x in xs]
+        w.run(lambda r, c: c.allreduce(xs[r].data_ptr(), xs[r].data_ptr(), n, N.INT32, N.SUM))
+        torch.cuda.synchronize()
+        w.check()
+        total = int(xs[0].sum(dtype=torch.int64).item())
+        assert (sum(locals_) - total) % (1 << 32) == 0, "checksum of checksums mismatch"
+        assert torch.equal(xs[0], xs[1]), "ranks must hold identical bits"
+        ys = [x.clone() for x in xs]
+        w.run(lambda r, c: c.allreduce(ys[r].data_ptr(), ys[r].data_ptr(), n, N.INT32, N.MAX))
+        torch.cuda.synchronize()
+        assert torch.equal(ys[0], xs[0]) and torch.equal(ys[1], xs[0]), "MAX over identical buffers must be idempotent"
+        del ys
+        fs = [torch.ones(n, device="cuda") for _ in range(W)]
+        w.run(lambda r, c: c.allreduce(fs[r].data_ptr(), fs[r].data_ptr(), n, N.FLOAT32, N.SUM))
+        torch.cuda.synchronize()
+        w.check()
+        assert all(bool((f == float(W)).all().item()) for f in fs)
+    finally:
+        w.destroy()
