@@ -19,7 +19,7 @@
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("[r%d] CUDA error %s at %s:%d: %s\n", g_rank, #x, __FILE__, __LINE__, cudaGetErrorString(e_)); fflush(stdout); return -1; } } while (0)
 #define CU(x) do { CUresult e_ = (x); if (e_ != CUDA_SUCCESS) { const char* s_=nullptr; cuGetErrorString(e_, &s_); printf("[r%d] CU error %s at %s:%d: %d %s\n", g_rank, #x, __FILE__, __LINE__, (int)e_, s_?s_:"?"); fflush(stdout); return -1; } } while (0)
 
-static int g_rank = -1, g_world = 0, g_sock = -1;
+static int g_rank = -1, g_world = 0, g_sock = -1, g_exp = 0;
 
 // ---------- message passing with optional fd ----------
 static int send_msg(int sock, const void* buf, size_t len, int fd) {
@@ -153,6 +153,80 @@ __global__ void pingpong_kernel(volatile unsigned* my_flag, unsigned* peer_flag,
     }
   }
   *cycles = clock64() - t0;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// round-2 experiments (run with: tools/probe <ngpus> exp)
+// ---------------------------------------------------------------------------------------------
+// E2: CTAs [0, n_nvls) reduce+broadcast through the switch, CTAs [n_nvls, grid) push unicast to peers.
+__global__ void __launch_bounds__(512) mix_kernel(float4* mc, size_t nvls_begin16, size_t nvls_n16, int n_nvls,
+                                                  Ptrs peers, int rank, int world, const uint4* __restrict__ src,
+                                                  size_t p2p_dst_off16, size_t p2p_n16) {
+  if ((int)blockIdx.x < n_nvls) {
+    size_t stride = (size_t)n_nvls * blockDim.x;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvls_n16; i += stride) {
+      float4 v;
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc + nvls_begin16 + i) : "memory");
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                   :: "l"(mc + nvls_begin16 + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+  } else {
+    int nb = gridDim.x - n_nvls, b = blockIdx.x - n_nvls;
+    size_t per_peer = p2p_n16 / (world - 1);
+    for (int k = 1; k < world; k++) {
+      int j = (rank + k) % world;
+      uint4* dst = (uint4*)peers.p[j] + p2p_dst_off16 + (size_t)rank * per_peer;
+      const uint4* s = src + (size_t)(k - 1) * per_peer;
+      size_t stride = (size_t)nb * blockDim.x;
+      size_t i = b * (size_t)blockDim.x + threadIdx.x;
+      for (; i + 3 * stride < per_peer; i += 4 * stride) {
+        uint4 v0 = s[i], v1 = s[i + stride], v2 = s[i + 2 * stride], v3 = s[i + 3 * stride];
+        dst[i] = v0; dst[i + stride] = v1; dst[i + 2 * stride] = v2; dst[i + 3 * stride] = v3;
+      }
+      for (; i < per_peer; i += stride) dst[i] = s[i];
+    }
+  }
+}
+// E3: cost of a system-scope fence while the other warps of the CTA keep streaming stores to a peer.
+__global__ void __launch_bounds__(512) fence_kernel(uint4* peer_dst, const uint4* __restrict__ src, size_t n16, unsigned* peer_flag,
+                                                   int iters, int do_stream, long long* cycles_out) {
+  __shared__ volatile int done;
+  if (threadIdx.x == 0) done = 0;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) {
+      long long t0 = clock64();
+      for (int k = 1; k <= iters; k++) {
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(peer_flag + blockIdx.x), "r"((unsigned)k) : "memory");
+      }
+      long long t1 = clock64();
+      if (blockIdx.x == 0) *cycles_out = (t1 - t0) / iters;
+      done = 1;
+    }
+  } else if (do_stream) {
+    size_t per = n16 / gridDim.x, base = per * blockIdx.x;
+    size_t i = threadIdx.x - 32;
+    while (!done) {
+      peer_dst[base + i] = src[base + i];
+      i += 480; if (i >= per) i = threadIdx.x - 32;
+    }
+  }
+}
+// E4: packed data+flag (one 16-byte store, no fence) ping-pong
+__global__ void ll_pingpong_kernel(uint4* my_slot, uint4* peer_slot, int iters, int first) {
+  for (int k = 1; k <= iters; k++) {
+    uint4 out = make_uint4(0xabcd0000u + k, 0x1234u, 0x5678u, (unsigned)k);
+    if (first) {
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(peer_slot), "r"(out.x), "r"(out.y), "r"(out.z), "r"(out.w) : "memory");
+      uint4 v; do { asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(my_slot) : "memory"); } while (v.w != (unsigned)k);
+    } else {
+      uint4 v; do { asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(my_slot) : "memory"); } while (v.w != (unsigned)k);
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(peer_slot), "r"(out.x), "r"(out.y), "r"(out.z), "r"(out.w) : "memory");
+    }
+  }
 }
 
 static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
@@ -369,6 +443,63 @@ static int child_main(int isolate) {
         printf("[r%d] PROBE multimem fused RS+AG (no sync) grid=%dxSMs: algBW %.1f GB/s busBW %.1f GB/s\n", g_rank, mult, 5.0 * BYTES / time_ms(e0, e1) / 1e6,
                5.0 * BYTES / time_ms(e0, e1) / 1e6 * 2 * (g_world - 1) / g_world);
       }
+      if (g_exp) {
+        // ---- E1: how many CTAs does NVLS need? (fused ld_reduce+st of the own 1/W slice)
+        for (int g2 : {8, 16, 32, 64, 148, 296}) {
+          if (barrier()) return -1;
+          CK(cudaEventRecord(e0)); for (int it = 0; it < 5; it++) mc_allreduce_kernel<<<g2, 512>>>((float4*)mcva, g_rank * sl16, sl16);
+          CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+          if (g_rank == 0) printf("[r0] EXP E1 nvls grid=%d CTAs: algBW %.1f GB/s\n", g2, 5.0 * BYTES / time_ms(e0, e1) / 1e6);
+        }
+        // ---- E5: one source: rank 0 alone multicasts the whole buffer
+        if (barrier()) return -1;
+        CK(cudaEventRecord(e0));
+        if (g_rank == 0) for (int it = 0; it < 5; it++) mc_st_kernel<<<G, 512>>>((float4*)mcva, (const float4*)tmp, BYTES / 16);
+        CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+        if (g_rank == 0) printf("[r0] EXP E5 single-source multimem.st: %.1f GB/s out of the root\n", 5.0 * BYTES / time_ms(e0, e1) / 1e6);
+        // ---- E2: does unicast P2P traffic ride beside NVLS?  first half of the buffer: NVLS; second half: P2P landing zone
+        if (g_world > 2) {
+          Ptrs ps; for (int j = 0; j < g_world; j++) ps.p[j] = (const uint4*)peers[j].va;
+          size_t half16 = BYTES / 32, nsl16 = half16 / g_world;      // NVLS slice per rank inside the first half
+          size_t p2p16 = half16 / g_world / (g_world - 1) * (g_world - 1);  // bytes each rank pushes in total (lands in 1/W of the peers' second half)
+          struct { int n_nvls, n_p2p; size_t nv, np; const char* name; } cfg[] = {
+              {32, 0, nsl16, 0, "NVLS only (32 CTAs)"}, {0, 264, 0, p2p16, "P2P only (264 CTAs)"}, {32, 264, nsl16, p2p16, "both"}};
+          for (auto& c : cfg) {
+            if (barrier()) return -1;
+            CK(cudaEventRecord(e0));
+            for (int it = 0; it < 5; it++)
+              mix_kernel<<<c.n_nvls + c.n_p2p, 512>>>((float4*)mcva, g_rank * nsl16, c.nv, c.n_nvls, ps, g_rank, g_world, (const uint4*)tmp, half16, c.np);
+            CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+            double ms = time_ms(e0, e1) / 5;
+            if (g_rank == 0) printf("[r0] EXP E2 %-22s %.1f us  (NVLS algBW %.1f GB/s over %zu MB; P2P egress %.1f GB/s)\n", c.name, ms * 1e3,
+                                    c.nv ? half16 * 16.0 / ms / 1e6 : 0.0, half16 * 16 >> 20, c.np ? c.np * 16.0 / ms / 1e6 : 0.0);
+          }
+        }
+        // ---- E3: fence cost with and without a concurrent store stream to the peer (148 CTAs)
+        {
+          long long* d_cyc; CK(cudaMalloc(&d_cyc, 8));
+          unsigned* pflag = (unsigned*)((char*)peers[peer].va + (BYTES / 2));   // scratch words inside the landing zone
+          for (int stream = 0; stream < 2; stream++) {
+            if (barrier()) return -1;
+            fence_kernel<<<prop.multiProcessorCount, 512>>>((uint4*)peers[peer].va + BYTES / 32 + 4096, (const uint4*)tmp, (BYTES / 64), pflag, 200, stream, d_cyc);
+            long long cyc = 0; CK(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
+            if (g_rank == 0) printf("[r0] EXP E3 fence.acq_rel.sys + flag store, %s: %lld cycles each (%.2f us at %.0f MHz)\n",
+                                    stream ? "other warps streaming stores to the peer" : "quiet SM", cyc, cyc / (prop.clockRate / 1e3), prop.clockRate / 1e3);
+          }
+          cudaFree(d_cyc);
+        }
+        // ---- E4: packed data+flag round trip (no fence) between rank 0 and 1
+        if (g_world >= 2) {
+          CK(cudaMemset((void*)mine.va, 0, 4096)); CK(cudaDeviceSynchronize()); if (barrier()) return -1;
+          if (g_rank < 2) {
+            CK(cudaEventRecord(e0));
+            ll_pingpong_kernel<<<1, 1>>>((uint4*)mine.va, (uint4*)peers[g_rank ^ 1].va, 1000, g_rank == 0);
+            CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+            printf("[r%d] EXP E4 packed 16-byte data+flag ping-pong: %.2f us per round trip\n", g_rank, time_ms(e0, e1));
+          }
+          if (barrier()) return -1;
+        }
+      }
       cudaFree(tmp);
     } else printf("[r%d] PROBE multicast path NOT usable\n", g_rank);
     fflush(stdout);
@@ -380,6 +511,7 @@ static int child_main(int isolate) {
 
 int main(int argc, char** argv) {
   int W = argc > 1 ? atoi(argv[1]) : 2; int isolate = argc > 2 && !strcmp(argv[2], "isolate");
+  g_exp = argc > 2 && !strcmp(argv[2], "exp");
   std::vector<int> socks(W); std::vector<pid_t> pids(W);
   for (int r = 0; r < W; r++) {
     int sv[2]; if (socketpair(AF_UNIX, SOCK_STREAM, 0, sv)) { perror("socketpair"); return 1; }
