@@ -9,7 +9,10 @@ from ant_ray_b200.types import Backend, ReduceOp
 
 
 class Worker:
-    """CPU worker (gloo backend, registered from the oracle package)."""
+    """CPU worker (gloo backend, registered from the oracle package).
+
+    `do_<op>` methods run one collective on the worker's buffers and return the buffer(s) the op wrote;
+    `report_*` methods expose the group-introspection API."""
 
     def __init__(self):
         from oracle import gloo_group
@@ -18,13 +21,10 @@ class Worker:
         self.buffer = None
         self.list_buffer = None
 
+    # ---- buffers ------------------------------------------------------------------------------
     def init_tensors(self):
         self.buffer = np.ones((10,), dtype=np.float32)
         self.list_buffer = [np.ones((10,), dtype=np.float32) for _ in range(2)]
-        return True
-
-    def init_group(self, world_size, rank, backend=Backend.B200, group_name="default"):
-        col.init_collective_group(world_size, rank, backend, group_name)
         return True
 
     def set_buffer(self, data):
@@ -35,48 +35,49 @@ class Worker:
         return self.buffer
 
     def set_list_buffer(self, list_of_arrays, copy=False):
-        if copy:
-            self.list_buffer = [t.copy() if isinstance(t, np.ndarray) else t.clone().detach() for t in list_of_arrays]
-        else:
-            self.list_buffer = list_of_arrays
+        self.list_buffer = [(t.copy() if isinstance(t, np.ndarray) else t.clone().detach()) for t in list_of_arrays] if copy else list_of_arrays
         return self.list_buffer
 
-    def do_allreduce(self, group_name="default", op=ReduceOp.SUM):
-        col.allreduce(self.buffer, group_name, op)
-        return self._ret(self.buffer)
-
-    def do_reduce(self, group_name="default", dst_rank=0, op=ReduceOp.SUM):
-        col.reduce(self.buffer, dst_rank, group_name, op)
-        return self._ret(self.buffer)
-
-    def do_broadcast(self, group_name="default", src_rank=0):
-        col.broadcast(self.buffer, src_rank, group_name)
-        return self._ret(self.buffer)
-
-    def do_allgather(self, group_name="default"):
-        col.allgather(self.list_buffer, self.buffer, group_name)
-        return [self._ret(t) for t in self.list_buffer]
-
-    def do_reducescatter(self, group_name="default", op=ReduceOp.SUM):
-        col.reducescatter(self.buffer, self.list_buffer, group_name, op)
-        return self._ret(self.buffer)
-
-    def do_send(self, group_name="default", dst_rank=0):
-        col.send(self.buffer, dst_rank, group_name)
-        return self._ret(self.buffer)
-
-    def do_recv(self, group_name="default", src_rank=0):
-        col.recv(self.buffer, src_rank, group_name)
-        return self._ret(self.buffer)
-
-    def do_barrier(self, group_name="default"):
-        col.barrier(group_name)
+    # ---- group lifecycle ----------------------------------------------------------------------
+    def init_group(self, world_size, rank, backend=Backend.B200, group_name="default"):
+        col.init_collective_group(world_size, rank, backend, group_name)
         return True
 
     def destroy_group(self, group_name="default"):
         col.destroy_collective_group(group_name)
         return True
 
+    # ---- collectives --------------------------------------------------------------------------
+    def _run(self, fn, *args, out="buffer"):
+        fn(*args)
+        return [self._ret(t) for t in self.list_buffer] if out == "list" else self._ret(self.buffer)
+
+    def do_allreduce(self, group_name="default", op=ReduceOp.SUM):
+        return self._run(col.allreduce, self.buffer, group_name, op)
+
+    def do_reduce(self, group_name="default", dst_rank=0, op=ReduceOp.SUM):
+        return self._run(col.reduce, self.buffer, dst_rank, group_name, op)
+
+    def do_broadcast(self, group_name="default", src_rank=0):
+        return self._run(col.broadcast, self.buffer, src_rank, group_name)
+
+    def do_allgather(self, group_name="default"):
+        return self._run(col.allgather, self.list_buffer, self.buffer, group_name, out="list")
+
+    def do_reducescatter(self, group_name="default", op=ReduceOp.SUM):
+        return self._run(col.reducescatter, self.buffer, self.list_buffer, group_name, op)
+
+    def do_send(self, group_name="default", dst_rank=0):
+        return self._run(col.send, self.buffer, dst_rank, group_name)
+
+    def do_recv(self, group_name="default", src_rank=0):
+        return self._run(col.recv, self.buffer, src_rank, group_name)
+
+    def do_barrier(self, group_name="default"):
+        col.barrier(group_name)
+        return True
+
+    # ---- introspection ------------------------------------------------------------------------
     def report_rank(self, group_name="default"):
         return col.get_rank(group_name)
 
