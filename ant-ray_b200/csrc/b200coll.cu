@@ -195,7 +195,7 @@ extern "C" void b200c_default_config(b200c_config_t* cfg) {
   cfg->oneshot_max_bytes = 0;  // 0 = pick by world size in b200c_comm_create
   cfg->nvls_min_bytes = (1ull << 20) + 1;
   cfg->nvls_pipe_min_bytes = 0;  // off by default until validated on the target box
-  cfg->timeout_ms = 30000;
+  cfg->timeout_ms = 600000;  // a slow peer (data loading, first-step autotuning skew) is not a dead peer
 }
 
 static int ensure_driver() {
@@ -272,7 +272,7 @@ extern "C" int b200c_comm_create(int rank, int world, int device, const b200c_co
   if (cfg.p2p_slots == 0 || cfg.p2p_slots > (uint32_t)kMaxCells) return fail(B200C_EINVAL, "p2p_slots %u not in [1, %d]", cfg.p2p_slots, kMaxCells);
   if (cfg.p2p_slot_bytes < 512 || cfg.p2p_slot_bytes % 16) return fail(B200C_EINVAL, "p2p_slot_bytes must be a multiple of 16 and >= 512");
   if (cfg.staging_bytes < (1u << 16) || cfg.staging_bytes % 4096) return fail(B200C_EINVAL, "staging_bytes must be a multiple of 4096 and >= 64 KiB");
-  if (cfg.timeout_ms == 0) cfg.timeout_ms = 30000;
+  if (cfg.timeout_ms == 0) cfg.timeout_ms = 600000;
   // measured crossovers (profiles/r01_sweep_*): W=2 one-shot wins to 8 MiB; W=8 one-shot 23 us vs NVLS 28 us at 1 MiB
   if (cfg.oneshot_max_bytes == 0) cfg.oneshot_max_bytes = world <= 2 ? (8ull << 20) : (1ull << 20);
 

@@ -437,6 +437,7 @@ def main():
     device = torch.device("cuda", local)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29533")
+    os.environ.setdefault("B200COLL_TIMEOUT_MS", "60000")  # a benchmark should fail fast, not wait out the production default
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
     torch.backends.cudnn.benchmark = True
     N.load()

@@ -94,7 +94,7 @@ typedef struct {
   uint64_t oneshot_max_bytes;  /* AUTO: message <= this -> one-shot */
   uint64_t nvls_min_bytes;     /* AUTO: message >= this and multicast bound -> NVLS */
   uint64_t nvls_pipe_min_bytes;/* AUTO: staged NVLS pieces >= this use the pipelined kernel (0 = never) */
-  uint64_t timeout_ms;         /* device-side bounded spin; 0 = default (30 s) */
+  uint64_t timeout_ms;         /* device-side bounded spin; 0 = default (600 s; NCCL's watchdog default is of that order) */
 } b200c_config_t;
 
 typedef struct {
