@@ -32,7 +32,7 @@ INT8, UINT8, INT32, UINT32, INT64, UINT64, FLOAT16, FLOAT32, FLOAT64, BFLOAT16 =
 # b200c_redop_t (ncclRedOp_t numbering)
 SUM, PROD, MAX, MIN, AVG = range(5)
 # b200c_algo_t
-ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS, ALGO_NVLS_PIPE = range(5)
+ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS, ALGO_NVLS_PIPE, ALGO_LL = range(6)
 # b200c_share_mode_t
 SHARE_VMM_FD, SHARE_LEGACY_IPC = 0, 1
 MAX_RANKS = 8
@@ -42,7 +42,9 @@ class Config(Structure):
     _fields_ = [("struct_size", c_uint32), ("share_mode", c_int32), ("staging_bytes", c_uint64),
                 ("symmetric_bytes", c_uint64), ("p2p_slot_bytes", c_uint64), ("p2p_slots", c_uint32),
                 ("max_blocks", c_uint32), ("oneshot_max_bytes", c_uint64), ("nvls_min_bytes", c_uint64),
-                ("nvls_pipe_min_bytes", c_uint64), ("timeout_ms", c_uint64)]
+                ("nvls_pipe_min_bytes", c_uint64), ("timeout_ms", c_uint64), ("granule_bytes", c_uint64),
+                ("ll_max_bytes", c_uint64), ("bcast_rounds_min_bytes", c_uint64), ("nvls_blocks", c_uint32),
+                ("reserved0", c_uint32)]
 
 
 class Props(Structure):
@@ -119,7 +121,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here means header and library disagree
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.b200c_version() < 100:
+    if lib.b200c_version() < 200:
         raise ImportError("libb200coll.so is older than this Python package")
     _lib = lib
     return lib

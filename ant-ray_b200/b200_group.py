@@ -127,6 +127,10 @@ def make_config(**overrides):
         "B200COLL_ONESHOT_MAX_BYTES": ("oneshot_max_bytes", int),
         "B200COLL_NVLS_MIN_BYTES": ("nvls_min_bytes", int),
         "B200COLL_NVLS_PIPE_MIN_BYTES": ("nvls_pipe_min_bytes", int),
+        "B200COLL_GRANULE_BYTES": ("granule_bytes", int),
+        "B200COLL_LL_MAX_BYTES": ("ll_max_bytes", int),
+        "B200COLL_BCAST_ROUNDS_MIN_BYTES": ("bcast_rounds_min_bytes", int),
+        "B200COLL_NVLS_BLOCKS": ("nvls_blocks", int),
         "B200COLL_TIMEOUT_MS": ("timeout_ms", int),
         "B200COLL_P2P_SLOT_BYTES": ("p2p_slot_bytes", int),
         "B200COLL_P2P_SLOTS": ("p2p_slots", int),

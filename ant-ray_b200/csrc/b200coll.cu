@@ -130,7 +130,7 @@ struct b200c_comm {
   int sm_count = 148;
   // arena
   size_t arena_bytes = 0, gran = 0;
-  size_t off_staging = 0, off_p2p = 0, off_sym = 0, sym_bytes = 0;
+  size_t off_staging = 0, off_p2p = 0, off_ll = 0, ll_words = 0, off_sym = 0, sym_bytes = 0;
   uint64_t layout_hash = 0;
   bool vmm = true;
   CUmemGenericAllocationHandle own_handle = 0;
@@ -148,7 +148,9 @@ struct b200c_comm {
   bool ready = false, destroyed = false;
   uint32_t seq = 0;
   bool bcast_mc = false;   // broadcast through one multicast store stream (wins for W > 2)
-  uint32_t pipe_base = 0;  // flag epoch of the pipelined kernels (advanced by the sub-tile count of each op)
+  uint32_t pipe_base = 0;  // flag epoch of the round-pipelined kernels (advanced by the round count of each op)
+  uint32_t ll_seq = 0;     // LL op counter (flag value of the packed stores; region half = ll_seq & 1)
+  int local_scale_ctas_per_sm = 0;
   uint32_t send_cells[kMaxRanks] = {};
   uint32_t recv_cells[kMaxRanks] = {};
   DevComm dev{};
@@ -194,8 +196,12 @@ extern "C" void b200c_default_config(b200c_config_t* cfg) {
   cfg->max_blocks = 296;
   cfg->oneshot_max_bytes = 0;  // 0 = pick by world size in b200c_comm_create
   cfg->nvls_min_bytes = (1ull << 20) + 1;
-  cfg->nvls_pipe_min_bytes = 0;  // off by default until validated on the target box
+  cfg->nvls_pipe_min_bytes = 8ull << 20;  // staged NVLS pieces from 8 MiB up run round-pipelined
   cfg->timeout_ms = 600000;  // a slow peer (data loading, first-step autotuning skew) is not a dead peer
+  cfg->granule_bytes = 32ull << 10;
+  cfg->ll_max_bytes = 32ull << 10;
+  cfg->bcast_rounds_min_bytes = 4ull << 20;
+  cfg->nvls_blocks = 0;
 }
 
 static int ensure_driver() {
@@ -273,6 +279,10 @@ extern "C" int b200c_comm_create(int rank, int world, int device, const b200c_co
   if (cfg.p2p_slot_bytes < 512 || cfg.p2p_slot_bytes % 16) return fail(B200C_EINVAL, "p2p_slot_bytes must be a multiple of 16 and >= 512");
   if (cfg.staging_bytes < (1u << 16) || cfg.staging_bytes % 4096) return fail(B200C_EINVAL, "staging_bytes must be a multiple of 4096 and >= 64 KiB");
   if (cfg.timeout_ms == 0) cfg.timeout_ms = 600000;
+  if (cfg.granule_bytes == 0) cfg.granule_bytes = 32ull << 10;
+  if (cfg.granule_bytes % 16384) return fail(B200C_EINVAL, "granule_bytes must be a multiple of 16 KiB");
+  if (cfg.ll_max_bytes > (1ull << 20)) return fail(B200C_EINVAL, "ll_max_bytes must be <= 1 MiB");
+  if (cfg.nvls_blocks > (uint32_t)kMaxBlocks) return fail(B200C_EINVAL, "nvls_blocks %u > %d", cfg.nvls_blocks, kMaxBlocks);
   // measured crossovers (profiles/r01_sweep_*): W=2 one-shot wins to 8 MiB; W=8 one-shot 23 us vs NVLS 28 us at 1 MiB
   if (cfg.oneshot_max_bytes == 0) cfg.oneshot_max_bytes = world <= 2 ? (8ull << 20) : (1ull << 20);
 
@@ -293,7 +303,10 @@ extern "C" int b200c_comm_create(int rank, int world, int device, const b200c_co
   c->off_staging = kPadBytes;
   c->off_p2p = c->off_staging + 2 * cfg.staging_bytes;
   size_t p2p_bytes = world > 1 ? (size_t)kMaxRanks * cfg.p2p_slots * cfg.p2p_slot_bytes : 0;
-  c->off_sym = round_up(c->off_p2p + p2p_bytes, 2ull << 20);
+  c->off_ll = round_up(c->off_p2p + p2p_bytes, 4096);
+  c->ll_words = world > 1 ? round_up((cfg.ll_max_bytes + 3) / 4, 4) : 0;   // whole 16-byte vectors
+  size_t ll_bytes = 2 * (size_t)kMaxRanks * c->ll_words * 8;
+  c->off_sym = round_up(c->off_ll + ll_bytes, 2ull << 20);
   size_t want = c->off_sym + cfg.symmetric_bytes;
   size_t gran = 2ull << 20;
   if (c->vmm) {
@@ -315,7 +328,8 @@ extern "C" int b200c_comm_create(int rank, int world, int device, const b200c_co
   c->arena_bytes = round_up(want, gran);
   c->sym_bytes = c->arena_bytes - c->off_sym;
   c->layout_hash = (uint64_t)cfg.staging_bytes * 1000003ull ^ (uint64_t)cfg.p2p_slot_bytes * 10007ull ^ (uint64_t)cfg.p2p_slots * 101ull ^
-                   (uint64_t)c->arena_bytes ^ ((uint64_t)cfg.max_blocks << 48) ^ ((uint64_t)world << 56);
+                   (uint64_t)c->arena_bytes ^ ((uint64_t)cfg.max_blocks << 48) ^ ((uint64_t)world << 56) ^
+                   (uint64_t)cfg.ll_max_bytes * 7919ull ^ (uint64_t)cfg.granule_bytes * 31ull ^ ((uint64_t)cfg.nvls_blocks << 36);
 
   if (c->vmm) {
     CUmemAllocationProp ap = alloc_prop(c->cudev);
@@ -331,6 +345,7 @@ extern "C" int b200c_comm_create(int rank, int world, int device, const b200c_co
   }
   c->imported[rank] = true;
   RT(cudaMemset(c->arena[rank], 0, kPadBytes));
+  if (ll_bytes) RT(cudaMemset(c->arena[rank] + c->off_ll, 0, ll_bytes));  // LL flags start at 0 (never a valid ll_seq)
   RT(cudaHostAlloc(reinterpret_cast<void**>(&c->status_host), sizeof(Status), cudaHostAllocMapped | cudaHostAllocPortable));
   memset((void*)c->status_host, 0, sizeof(Status));
   RT(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->status_dev), (void*)c->status_host, 0));
@@ -456,6 +471,8 @@ extern "C" int b200c_comm_ready(b200c_comm_t* c) {
   d.off_p2p = c->off_p2p;
   d.p2p_cell_bytes = c->cfg.p2p_slot_bytes;
   d.p2p_cells = (int)c->cfg.p2p_slots;
+  d.off_ll = c->off_ll;
+  d.ll_words = c->ll_words;
   // a single multimem.st stream leaves the root at ~340 GB/s (measured), a unicast push at ~690 GB/s:
   // multicast pays off as soon as there is more than one receiver
   c->bcast_mc = c->world > 2;
@@ -547,22 +564,48 @@ static int check_ready(b200c_comm* c) {
   if (c->status_host->error) return b200c_comm_check(c);
   return B200C_OK;
 }
-static int launch_check(const char* what) {
+// A launch that fails after its peers may already have launched the same op leaves this rank behind:
+// poison the communicator so the failure is loud on every later call instead of a silent divergence.
+static int launch_check(b200c_comm* c, const char* what) {
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(B200C_ECUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+  if (e != cudaSuccess) {
+    if (c && c->status_host && c->status_host->error == 0) { c->status_host->error = B200C_ECUDA; c->status_host->err_seq = c->seq + 1; }
+    return fail(B200C_ECUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+  }
   g_launches.fetch_add(1);
   return B200C_OK;
 }
-// split `units` elements (vector width vec) over blocks of at least min_tile_bytes
-static void plan_tiles(size_t units, size_t elem_size, size_t vec, uint32_t max_blocks, size_t min_tile_bytes, size_t* tile, int* grid) {
+// Block-cyclic plan for an extent of `units` elements (vector width `vec`).
+//   small extents: one contiguous granule per block of at least min_tile_bytes (more blocks = lower latency);
+//   large extents: fixed granule of `granule_bytes`, `max_blocks` blocks, each looping with stride grid * granule.
+static void plan_tiles(size_t units, size_t elem_size, size_t vec, uint32_t max_blocks, size_t min_tile_bytes, size_t granule_bytes,
+                       size_t* tile, int* grid) {
   if (units == 0) { *tile = vec; *grid = 1; return; }
   size_t bytes = units * elem_size;
   size_t nb = (bytes + min_tile_bytes - 1) / min_tile_bytes;
   if (nb < 1) nb = 1;
   if (nb > max_blocks) nb = max_blocks;
   size_t t = round_up((units + nb - 1) / nb, vec);
+  if (t * elem_size > granule_bytes) t = granule_bytes / elem_size;  // granule_bytes is a multiple of 16 KiB, hence of vec
+  size_t g = (units + t - 1) / t;
   *tile = t;
-  *grid = (int)((units + t - 1) / t);
+  *grid = (int)(g < max_blocks ? g : max_blocks);
+}
+// Plan for the round-pipelined kernels: at least ~4 rounds per block when the extent allows it, so that
+// the software pipeline has something to overlap; granules of 8 KiB .. granule_bytes.
+static void plan_rounds(size_t units, size_t elem_size, size_t vec, uint32_t max_blocks, size_t granule_bytes, size_t* tile, int* grid,
+                        uint32_t* rounds) {
+  size_t bytes = units * elem_size;
+  size_t tb = bytes / ((size_t)max_blocks * 4) / 8192 * 8192;
+  if (tb < 8192) tb = 8192;
+  if (tb > granule_bytes) tb = granule_bytes;
+  size_t t = tb / elem_size;
+  (void)vec;
+  size_t g = (units + t - 1) / t;
+  if (g < 1) g = 1;
+  *tile = t;
+  *grid = (int)(g < max_blocks ? g : max_blocks);
+  *rounds = (uint32_t)((units + (size_t)*grid * t - 1) / ((size_t)*grid * t));
 }
 static uint32_t make_sig(int opcode, int dtype, int op, size_t n, int root, int extra) {
   uint64_t h = 1469598103934665603ull;
@@ -570,12 +613,15 @@ static uint32_t make_sig(int opcode, int dtype, int op, size_t n, int root, int 
   for (int i = 0; i < 6; i++) { h ^= v[i]; h *= 1099511628211ull; }
   return ((uint32_t)(h ^ (h >> 32)) & 0x7fffffffu) | 1u;  // never 0 and never the 0xFFFFFFFF wildcard
 }
+// The op takes sequence number seq + 1; the counter itself only advances once the launch has succeeded
+// (commit_args), so a rejected call (EINVAL / EUNSUPPORTED before any launch) leaves the ranks aligned.
 static void base_args(b200c_comm* c, CollArgs* a) {
   memset(a, 0, sizeof *a);
   a->c = c->dev;
-  a->seq = ++c->seq;
+  a->seq = c->seq + 1;
   a->root = -1;
 }
+static void commit_args(b200c_comm* c, const CollArgs& a) { c->seq = a.seq; }
 static int launch_same_type(int dtype, int kind, int op, const CollArgs& a, int grid, cudaStream_t s) {
   switch (dtype) {
     case B200C_INT8: return launch_i8(kind, op, a, grid, s);
@@ -603,8 +649,20 @@ static void launch_mixed(int algo, const CollArgs& a, int grid, cudaStream_t s) 
 }
 template <typename TI, typename TW>
 static void launch_nvls(const CollArgs& a, int grid, cudaStream_t s, bool pipe) {
-  if (pipe) k_allreduce_nvls_pipe<TI, TW><<<grid, kThreads, 0, s>>>(a);
+  if (pipe) k_allreduce_nvls_rounds<TI, TW><<<grid, kThreads, 0, s>>>(a);
   else k_allreduce_nvls<TI, TW><<<grid, kThreads, 0, s>>>(a);
+}
+template <typename TI, typename TW>
+static int local_scale_grid(b200c_comm* c, size_t bytes) {
+  // no peers to wait for, so the grid is sized for HBM: one CTA per 32 KiB, but never more CTAs than are
+  // resident at once (a second, partial wave would idle part of the chip for a whole pass)
+  if (c->local_scale_ctas_per_sm == 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_local_scale<float, bf16_t>, kThreads, 0) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 2; }
+    c->local_scale_ctas_per_sm = nb;
+  }
+  size_t want = (bytes + 32767) / 32768, cap = (size_t)c->sm_count * c->local_scale_ctas_per_sm;
+  return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
 static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t count, int dtype, int wire, int op, float scale,
@@ -619,7 +677,7 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     if (!(dtype == B200C_FLOAT32 && (wire == B200C_BFLOAT16 || wire == B200C_FLOAT16))) return fail(B200C_EUNSUPPORTED, "wire dtype %d for buffer dtype %d", wire, dtype);
     if (op != B200C_SUM && op != B200C_AVG) return fail(B200C_EUNSUPPORTED, "compressed wire supports SUM/AVG only");
   }
-  if (algo < B200C_ALGO_AUTO || algo > B200C_ALGO_NVLS_PIPE) return fail(B200C_EINVAL, "bad algo %d", algo);
+  if (algo < B200C_ALGO_AUTO || algo > B200C_ALGO_LL) return fail(B200C_EINVAL, "bad algo %d", algo);
   if (op == B200C_AVG) { has_scale = 1; scale = 1.f / (float)c->world; }
   if (count == 0) return B200C_OK;
   DeviceGuard g(c->device);
@@ -630,10 +688,7 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     if (!has_scale && wire == dtype) { RT(cudaMemcpyAsync(recv, send, count * esz, cudaMemcpyDeviceToDevice, s)); return B200C_OK; }
     CollArgs a; memset(&a, 0, sizeof a);
     a.c = c->dev; a.in = send; a.out = recv; a.n = count; a.has_scale = has_scale; a.scale = scale;
-    // no peers to wait for, so the grid is sized for HBM, not for co-residency: up to 8 CTAs per SM,
-    // one CTA per 32 KiB of input
-    size_t want = (count * esz + 32767) / 32768;
-    int grid = (int)(want < 1 ? 1 : (want > (size_t)c->sm_count * 8 ? (size_t)c->sm_count * 8 : want));
+    int grid = local_scale_grid<float, bf16_t>(c, count * esz);
     switch (dtype * 16 + wire) {
       case B200C_FLOAT32 * 16 + B200C_FLOAT32: k_local_scale<float, float><<<grid, kThreads, 0, s>>>(a); break;
       case B200C_FLOAT32 * 16 + B200C_BFLOAT16: k_local_scale<float, bf16_t><<<grid, kThreads, 0, s>>>(a); break;
@@ -646,12 +701,15 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
         if (send != recv) RT(cudaMemcpyAsync(recv, send, count * esz, cudaMemcpyDeviceToDevice, s));
         return B200C_OK;
     }
-    return launch_check("local_scale");
+    return launch_check(c, "local_scale");
   }
 
   const bool nvls_ok = c->mc_arena && (op == B200C_SUM || op == B200C_AVG) &&
                        (wire == B200C_FLOAT32 || wire == B200C_BFLOAT16 || wire == B200C_FLOAT16);
   if ((algo == B200C_ALGO_NVLS || algo == B200C_ALGO_NVLS_PIPE) && !nvls_ok) return fail(B200C_EUNSUPPORTED, "NVLS needs a bound multicast object, SUM/AVG and f32/bf16/f16");
+  const bool ll_ok = wire == dtype && c->ll_words && count * esz <= c->ll_words * 4;
+  if (algo == B200C_ALGO_LL && !ll_ok) return fail(B200C_EUNSUPPORTED, "LL needs wire == dtype and at most %zu bytes (ll_max_bytes)", c->ll_words * 4);
+  const uint32_t nvls_cap = c->cfg.nvls_blocks ? c->cfg.nvls_blocks : c->cfg.max_blocks;
   const char* in = static_cast<const char*>(send);
   char* out = static_cast<char*>(recv);
   size_t done = 0;
@@ -662,7 +720,8 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     bool pipe = false;
     if (al == B200C_ALGO_NVLS_PIPE) { al = B200C_ALGO_NVLS; pipe = true; }
     if (al == B200C_ALGO_AUTO) {
-      if (bytes_left <= c->cfg.oneshot_max_bytes) al = B200C_ALGO_ONESHOT;
+      if (ll_ok && count * esz <= c->cfg.ll_max_bytes) al = B200C_ALGO_LL;
+      else if (bytes_left <= c->cfg.oneshot_max_bytes) al = B200C_ALGO_ONESHOT;
       else if (nvls_ok && W > 2 && bytes_left >= c->cfg.nvls_min_bytes) al = B200C_ALGO_NVLS;
       else al = B200C_ALGO_TWOSHOT;
     }
@@ -672,42 +731,46 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     a.has_scale = has_scale; a.scale = scale;
     size_t n;
     int grid;
+    uint32_t rounds = 0;
     // symmetric zero-copy NVLS: buffer lives in the symmetric region at the same offset everywhere
     bool sym = false;
     if (al == B200C_ALGO_NVLS && wire == dtype && send == recv && c->sym_bytes) {
       char* base = c->arena[c->rank] + c->off_sym;
       if (in >= base && in + count * esz <= base + c->sym_bytes && (((uintptr_t)a.in) & 15) == 0 && (left * esz) % 16 == 0) sym = true;
     }
-    if (al == B200C_ALGO_ONESHOT) {
+    if (al == B200C_ALGO_LL) {
+      n = left;
+      a.chunk = round_up(n, vec);
+      a.tile = vec;
+      a.ll_seq = c->ll_seq + 1;
+      size_t nvec = (n * esz + 15) / 16;
+      size_t nb = (nvec + kLLThreads - 1) / kLLThreads;
+      grid = (int)(nb < 1 ? 1 : (nb > c->cfg.max_blocks ? c->cfg.max_blocks : nb));
+    } else if (al == B200C_ALGO_ONESHOT) {
       size_t cap = c->cfg.staging_bytes / W / wsz / vec * vec;  // elements per slot
       n = left < cap ? left : cap;
       a.chunk = round_up(n, vec);
-      plan_tiles(n, wsz, vec, c->cfg.max_blocks, kMinTileBytes, &a.tile, &grid);
+      plan_tiles(n, wsz, vec, c->cfg.max_blocks, kMinTileBytes, c->cfg.granule_bytes, &a.tile, &grid);
     } else if (al == B200C_ALGO_TWOSHOT) {
       size_t cap_chunk = c->cfg.staging_bytes / W / wsz / vec * vec;
       size_t cap = cap_chunk * W;
       n = left < cap ? left : cap;
       a.chunk = round_up((n + W - 1) / W, vec);
-      plan_tiles(a.chunk, wsz, vec, c->cfg.max_blocks, kMinTileBytes, &a.tile, &grid);
+      plan_tiles(a.chunk, wsz, vec, c->cfg.max_blocks, kMinTileBytes, c->cfg.granule_bytes, &a.tile, &grid);
     } else {
-      // symmetric buffers need no staging, but a piece beyond the 256 MiB TLB reach runs ~6 % slower per byte
+      // symmetric buffers need no staging; pieces of at most 256 MiB keep the peers' TLB reach
       size_t cap = sym ? ((size_t)256 << 20) / wsz : c->cfg.staging_bytes / wsz / vec * vec;
       n = left < cap ? left : cap;
       a.chunk = round_up((n + W - 1) / W, vec);
       a.symmetric = sym ? 1 : 0;
       a.sym_off = sym ? (size_t)((const char*)a.in - c->arena[c->rank]) : 0;
-      plan_tiles(a.chunk, wsz, vec, c->cfg.max_blocks, kMinTileBytes, &a.tile, &grid);
       if (!sym && algo == B200C_ALGO_AUTO && c->cfg.nvls_pipe_min_bytes && n * wsz >= c->cfg.nvls_pipe_min_bytes) pipe = true;
       if (sym) pipe = false;  // nothing to overlap: the symmetric path has no staging copies
       if (pipe) {
-        // 16 KiB sub-tiles (two load batches per reduce-role thread) and >= 4 of them per CTA so the
-        // three roles actually overlap; the flag epoch advances by the largest sub-tile count.
-        const size_t sub_bytes = 16384;
-        a.sub = sub_bytes / wsz;
-        plan_tiles(a.chunk, wsz, vec, c->cfg.max_blocks, 4 * sub_bytes, &a.tile, &grid);
-        size_t kmax = (a.tile + a.sub - 1) / a.sub;
+        plan_rounds(a.chunk, wsz, vec, nvls_cap, c->cfg.granule_bytes, &a.tile, &grid, &rounds);
         a.pipe_base = c->pipe_base;
-        c->pipe_base += (uint32_t)kmax;
+      } else {
+        plan_tiles(a.chunk, wsz, vec, nvls_cap, kMinTileBytes, c->cfg.granule_bytes, &a.tile, &grid);
       }
     }
     a.n = n;
@@ -722,11 +785,15 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
       if (wire == B200C_BFLOAT16) launch_mixed<float, bf16_t>(al, a, grid, s);
       else launch_mixed<float, f16_t>(al, a, grid, s);
     } else {
-      rc = launch_same_type(dtype, al == B200C_ALGO_ONESHOT ? KIND_ONESHOT : KIND_TWOSHOT, op, a, grid, s);
+      int kind = al == B200C_ALGO_LL ? KIND_LL : (al == B200C_ALGO_ONESHOT ? KIND_ONESHOT : KIND_TWOSHOT);
+      rc = launch_same_type(dtype, kind, op, a, grid, s);
       if (rc) return rc;
     }
-    rc = launch_check("allreduce");
+    rc = launch_check(c, "allreduce");
     if (rc) return rc;
+    commit_args(c, a);
+    c->pipe_base += rounds;
+    if (al == B200C_ALGO_LL) c->ll_seq = a.ll_seq;
     done += n;
   }
   return B200C_OK;
@@ -773,12 +840,13 @@ extern "C" int b200c_reduce(b200c_comm_t* c, const void* send, void* recv, size_
     a.n = n; a.chunk = round_up(n, vec); a.root = root;
     if (op == B200C_AVG) { a.has_scale = 1; a.scale = 1.f / c->world; }
     int grid;
-    plan_tiles(n, esz, vec, c->cfg.max_blocks, kMinTileBytes, &a.tile, &grid);
+    plan_tiles(n, esz, vec, c->cfg.max_blocks, kMinTileBytes, c->cfg.granule_bytes, &a.tile, &grid);
     a.sig = make_sig(OPC_REDUCE, dtype, op, n, root, 0);
     rc = launch_same_type(dtype, KIND_REDUCE, op, a, grid, s);
     if (rc) return rc;
-    rc = launch_check("reduce");
+    rc = launch_check(c, "reduce");
     if (rc) return rc;
+    commit_args(c, a);
     done += n;
   }
   return B200C_OK;
@@ -812,12 +880,13 @@ extern "C" int b200c_reducescatter(b200c_comm_t* c, const void* const* send_ptrs
     a.n = n; a.chunk = round_up(n, vec);
     if (op == B200C_AVG) { a.has_scale = 1; a.scale = 1.f / c->world; }
     int grid;
-    plan_tiles(n, esz, vec, c->cfg.max_blocks, kMinTileBytes, &a.tile, &grid);
+    plan_tiles(n, esz, vec, c->cfg.max_blocks, kMinTileBytes, c->cfg.granule_bytes, &a.tile, &grid);
     a.sig = make_sig(OPC_REDUCESCATTER, dtype, op, n, -1, 0);
     rc = launch_same_type(dtype, KIND_REDUCESCATTER, op, a, grid, s);
     if (rc) return rc;
-    rc = launch_check("reducescatter");
+    rc = launch_check(c, "reducescatter");
     if (rc) return rc;
+    commit_args(c, a);
     done += n;
   }
   return B200C_OK;
@@ -849,11 +918,12 @@ extern "C" int b200c_allgather(b200c_comm_t* c, const void* send, void* const* r
     for (int j = 0; j < c->world; j++) a.out_ptrs[j] = static_cast<char*>(recv_ptrs[j]) + done;
     a.n = n; a.chunk = round_up(n, 16);
     int grid;
-    plan_tiles(n, 1, 16, c->cfg.max_blocks, kMinTileBytes, &a.tile, &grid);
+    plan_tiles(n, 1, 16, c->cfg.max_blocks, kMinTileBytes, c->cfg.granule_bytes, &a.tile, &grid);
     a.sig = make_sig(OPC_ALLGATHER, dtype, 0, n, -1, 0);
     k_allgather<<<grid, kThreads, 0, s>>>(a);
-    rc = launch_check("allgather");
+    rc = launch_check(c, "allgather");
     if (rc) return rc;
+    commit_args(c, a);
     done += n;
   }
   return B200C_OK;
@@ -869,20 +939,41 @@ extern "C" int b200c_broadcast(b200c_comm_t* c, void* buf, size_t count, int dty
   if (!buf) return fail(B200C_EINVAL, "null buffer");
   cudaStream_t s = (cudaStream_t)stream;
   DeviceGuard g(c->device);
+  const int W = c->world;
   size_t bytes = count * esz, cap = c->cfg.staging_bytes / 16 * 16, done = 0;
   while (done < bytes) {
     size_t n = bytes - done < cap ? bytes - done : cap;
     CollArgs a;
     base_args(c, &a);
     a.in = static_cast<char*>(buf) + done; a.out = static_cast<char*>(buf) + done;
-    a.n = n; a.chunk = round_up(n, 16); a.root = root;
-    a.symmetric = (c->mc_arena && c->bcast_mc && n >= 65536) ? 1 : 0;  // multicast store from the root (same choice on every rank)
+    a.n = n; a.root = root;
     int grid;
-    plan_tiles(n, 1, 16, c->cfg.max_blocks, kMinTileBytes, &a.tile, &grid);
+    uint32_t rounds = 0;
+    // every rank takes the same decision from (n, world, multicast): the buffer address is NOT part of it
+    // except through the alignment every rank checks alike for its own pointer — an unaligned root falls
+    // back inside the kernel only in the unicast/multicast modes, so rounds mode requires torch-style
+    // (>= 16-byte aligned) buffers on every rank and is skipped otherwise by the size test below.
+    const bool mc = c->mc_arena && c->bcast_mc;
+    const bool rounds_mode = mc && W > 2 && c->cfg.bcast_rounds_min_bytes && n >= c->cfg.bcast_rounds_min_bytes && n % 16 == 0;
+    if (rounds_mode && (((uintptr_t)a.in) & 15) != 0)
+      return fail(B200C_EINVAL, "broadcast of >= %llu bytes needs a 16-byte aligned buffer", (unsigned long long)c->cfg.bcast_rounds_min_bytes);
+    if (rounds_mode) {
+      a.chunk = round_up((n + W - 1) / W, 16);
+      plan_rounds(a.chunk, 1, 16, c->cfg.max_blocks, c->cfg.granule_bytes, &a.tile, &grid, &rounds);
+      a.pipe_base = c->pipe_base;
+      a.symmetric = 2;
+    } else {
+      a.chunk = round_up(n, 16);
+      a.symmetric = (mc && n >= 65536) ? 1 : 0;  // multicast store from the root (same choice on every rank)
+      plan_tiles(n, 1, 16, c->cfg.max_blocks, kMinTileBytes, c->cfg.granule_bytes, &a.tile, &grid);
+    }
     a.sig = make_sig(OPC_BROADCAST, dtype, 0, n, root, a.symmetric);
-    k_broadcast<<<grid, kThreads, 0, s>>>(a);
-    rc = launch_check("broadcast");
+    if (rounds_mode) k_broadcast_rounds<<<grid, kThreads, 0, s>>>(a);
+    else k_broadcast<<<grid, kThreads, 0, s>>>(a);
+    rc = launch_check(c, "broadcast");
     if (rc) return rc;
+    commit_args(c, a);
+    c->pipe_base += rounds;
     done += n;
   }
   return B200C_OK;
@@ -897,7 +988,10 @@ extern "C" int b200c_barrier(b200c_comm_t* c, b200c_stream_t stream) {
   base_args(c, &a);
   a.sig = make_sig(OPC_BARRIER, 0, 0, 0, -1, 0);
   k_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(a);
-  return launch_check("barrier");
+  rc = launch_check(c, "barrier");
+  if (rc) return rc;
+  commit_args(c, a);
+  return B200C_OK;
 }
 
 static int p2p_impl(b200c_comm* c, void* buf, size_t bytes, int peer, bool is_send, cudaStream_t s) {
@@ -916,14 +1010,16 @@ static int p2p_impl(b200c_comm* c, void* buf, size_t bytes, int peer, bool is_se
   if (ncells > 0x7fffffffull) return fail(B200C_EINVAL, "message too large for the cell ring");
   uint32_t* ctr = is_send ? &c->send_cells[peer] : &c->recv_cells[peer];
   a.first_cell = *ctr; a.ncells = (uint32_t)ncells;
-  *ctr += (uint32_t)ncells;
   // no block may wait on a cell that one of its own later iterations has to free: grid <= ring size
   uint32_t grid = (uint32_t)ncells;
   uint32_t lim = c->cfg.max_blocks < c->cfg.p2p_slots ? c->cfg.max_blocks : c->cfg.p2p_slots;
   if (grid > lim) grid = lim;
   if (is_send) k_send<<<grid, kThreads, 0, s>>>(a);
   else k_recv<<<grid, kThreads, 0, s>>>(a);
-  return launch_check(is_send ? "send" : "recv");
+  rc = launch_check(c, is_send ? "send" : "recv");
+  if (rc) return rc;
+  *ctr += (uint32_t)ncells;  // the ring position only advances once the kernel is really queued
+  return B200C_OK;
 }
 extern "C" int b200c_send(b200c_comm_t* c, const void* buf, size_t bytes, int peer, b200c_stream_t stream) {
   return p2p_impl(c, const_cast<void*>(buf), bytes, peer, true, (cudaStream_t)stream);

@@ -10,29 +10,27 @@ namespace b200c {
 // W output tensors (out_ptrs[j]).  Pure byte movement -> instantiated once (uint8_t).
 // broadcast: root pushes into slot 0 of every peer; peers copy out.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_allgather(CollArgs a) {
+__global__ void __launch_bounds__(kThreads) k_allgather(const __grid_constant__ CollArgs a) {
   const DevComm& c = a.c;
   const int r = c.rank, W = c.world;
   if (!coll_prologue(a)) return;
-  const size_t t0 = (size_t)blockIdx.x * a.tile;           // bytes
-  const size_t cnt = clip_count(t0, t0 + a.tile, a.n);     // n = bytes per rank
-  const size_t slot_bytes = a.chunk;
+  const size_t slot_bytes = a.chunk;                       // n = bytes per rank
   const uint8_t* in = static_cast<const uint8_t*>(a.in);
-  if (cnt) {
+  uint8_t* own_out = static_cast<uint8_t*>(a.out_ptrs[r]);
+  B200C_FOR_GRANULES(t0, t1, a, a.n) {
     for (int k = 1; k < W; k++) {
       int j = r + k; if (j >= W) j -= W;
-      copy_tile<uint8_t, false>(staging_ptr<uint8_t>(c, j, a.seq, (size_t)r * slot_bytes) + t0, in + t0, cnt);
+      copy_tile<uint8_t, false>(staging_ptr<uint8_t>(c, j, a.seq, (size_t)r * slot_bytes) + t0, in + t0, t1 - t0);
     }
-    uint8_t* own_out = static_cast<uint8_t*>(a.out_ptrs[r]);
-    if (own_out + t0 != in + t0) copy_tile<uint8_t, false>(own_out + t0, in + t0, cnt);
+    if (own_out != in) copy_tile<uint8_t, false>(own_out + t0, in + t0, t1 - t0);
   }
   block_signal_all(kOffFlagA, a.seq, c);
   if (!block_wait_all(my_flags(kOffFlagA, c), a.seq, c, 1)) return;
   check_signature(a);
-  if (cnt) {
+  B200C_FOR_GRANULES(t0, t1, a, a.n) {
     for (int k = 1; k < W; k++) {
       int j = r + k; if (j >= W) j -= W;
-      copy_tile<uint8_t, true>(static_cast<uint8_t*>(a.out_ptrs[j]) + t0, staging_ptr<uint8_t>(c, r, a.seq, (size_t)j * slot_bytes) + t0, cnt);
+      copy_tile<uint8_t, true>(static_cast<uint8_t*>(a.out_ptrs[j]) + t0, staging_ptr<uint8_t>(c, r, a.seq, (size_t)j * slot_bytes) + t0, t1 - t0);
     }
   }
 }
@@ -40,33 +38,37 @@ __global__ void __launch_bounds__(kThreads) k_allgather(CollArgs a) {
 __device__ __forceinline__ void multimem_st16_bytes(void* p, uint4 v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// nv 16-byte vectors: src (plain or staging) -> multicast address
+template <bool SRC_BYPASS>
+__device__ __forceinline__ void multicast_tile(char* mc, const uint4* s, size_t nv) {
+  size_t i = threadIdx.x;
+  for (; i + (size_t)(kUnroll - 1) * kThreads < nv; i += (size_t)kUnroll * kThreads) {
+    uint4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) v[u] = SRC_BYPASS ? ld_bypass16(s + i + (size_t)u * kThreads) : s[i + (size_t)u * kThreads];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) multimem_st16_bytes(mc + (i + (size_t)u * kThreads) * 16, v[u]);
+  }
+  for (; i < nv; i += kThreads) multimem_st16_bytes(mc + i * 16, SRC_BYPASS ? ld_bypass16(s + i) : s[i]);
+}
 
-// a.symmetric != 0 selects the multicast variant: the root stores each 16-byte vector ONCE to the
-// multicast address of staging slot 0 and the NVSwitch replicates it into every rank's arena
-// (egress S instead of (W-1)*S); the sub-vector tail and unaligned sources go by unicast stores.
-__global__ void __launch_bounds__(kThreads) k_broadcast(CollArgs a) {
+// a.symmetric selects the variant:
+//   0  unicast: the root pushes every granule into slot 0 of every peer (egress (W-1)*S);
+//   1  root multicast: the root stores each 16-byte vector ONCE to the multicast address of staging
+//      slot 0 and the NVSwitch replicates it (egress S); the sub-vector tail and unaligned sources go
+//      by unicast stores.
+__global__ void __launch_bounds__(kThreads) k_broadcast(const __grid_constant__ CollArgs a) {
   const DevComm& c = a.c;
   const int r = c.rank, W = c.world, root = a.root;
   if (!coll_prologue(a)) return;
-  const size_t t0 = (size_t)blockIdx.x * a.tile;           // bytes
-  const size_t cnt = clip_count(t0, t0 + a.tile, a.n);
   if (r == root) {
-    if (cnt) {
+    B200C_FOR_GRANULES(t0, t1, a, a.n) {
+      const size_t cnt = t1 - t0;
       const uint8_t* src = static_cast<const uint8_t*>(a.in) + t0;
       size_t done = 0;
       if (a.symmetric && c.mc_arena && aligned16(src)) {
         const size_t nv = cnt / 16;
-        const uint4* s = reinterpret_cast<const uint4*>(src);
-        char* mc = c.mc_arena + c.off_staging + (size_t)(a.seq & 1) * c.staging_bytes + t0;
-        size_t i = threadIdx.x;
-        for (; i + (size_t)(kUnroll - 1) * kThreads < nv; i += (size_t)kUnroll * kThreads) {
-          uint4 v[kUnroll];
-#pragma unroll
-          for (int u = 0; u < kUnroll; u++) v[u] = s[i + (size_t)u * kThreads];
-#pragma unroll
-          for (int u = 0; u < kUnroll; u++) multimem_st16_bytes(mc + (i + (size_t)u * kThreads) * 16, v[u]);
-        }
-        for (; i < nv; i += kThreads) multimem_st16_bytes(mc + i * 16, s[i]);
+        multicast_tile<false>(c.mc_arena + c.off_staging + (size_t)(a.seq & 1) * c.staging_bytes + t0, reinterpret_cast<const uint4*>(src), nv);
         done = nv * 16;
       }
       if (done < cnt) {
@@ -80,12 +82,86 @@ __global__ void __launch_bounds__(kThreads) k_broadcast(CollArgs a) {
   } else {
     if (!block_wait_one(my_flags(kOffFlagA, c) + root, a.seq, c, root, 1)) return;
     check_signature(a);
-    if (cnt) copy_tile<uint8_t, true>(static_cast<uint8_t*>(a.out) + t0, staging_ptr<uint8_t>(c, r, a.seq, 0) + t0, cnt);
+    B200C_FOR_GRANULES(t0, t1, a, a.n) {
+      copy_tile<uint8_t, true>(static_cast<uint8_t*>(a.out) + t0, staging_ptr<uint8_t>(c, r, a.seq, 0) + t0, t1 - t0);
+    }
+  }
+}
+
+// Scatter + multicast-allgather broadcast for large messages (W > 2, multicast bound, 16-byte aligned,
+// n a multiple of 16): the message is cut into W rank chunks (a.chunk bytes).  Per round (one granule of
+// every chunk per block):
+//   root    : unicast-pushes the granule of chunk j into rank j's staging (its natural offset) and
+//             multicasts the granule of its own chunk straight from user memory; raises pipeA on every
+//             peer ("your granule has landed") and pipeB ("chunk[root] granule is everywhere");
+//   rank j  : waits pipeA(root), re-multicasts its granule from its staging to everybody, raises pipeB;
+//             then waits pipeB of every other rank for the previous round and copies that round's W
+//             granules out of its staging into the user buffer.
+// Root egress is ~S (unicast (W-1)/W*S + multicast S/W) instead of (W-1)*S, and — unlike the root-only
+// multicast — the W-1 receivers share the multicast work, so no single multimem.st stream is the bottleneck.
+__global__ void __launch_bounds__(kThreads) k_broadcast_rounds(const __grid_constant__ CollArgs a) {
+  const DevComm& c = a.c;
+  const int r = c.rank, W = c.world, root = a.root;
+  if (!coll_prologue(a)) return;
+  check_signature(a);
+  const size_t half_off = c.off_staging + (size_t)(a.seq & 1) * c.staging_bytes;
+  uint8_t* mine = reinterpret_cast<uint8_t*>(c.arena[r] + half_off);
+  char* mc = c.mc_arena + half_off;
+  const size_t first = (size_t)blockIdx.x * a.tile, step = (size_t)gridDim.x * a.tile;
+  if (first >= a.chunk) return;
+  const int R = (int)((a.chunk - first + step - 1) / step);
+  const int t = threadIdx.x;
+  auto lo_of = [&](int q) { return first + (size_t)q * step; };
+  auto hi_of = [&](int q) { size_t h = first + (size_t)q * step + a.tile; return h < a.chunk ? h : a.chunk; };
+  if (r == root) {
+    const uint8_t* src = static_cast<const uint8_t*>(a.in);
+    for (int q = 0; q < R; q++) {
+      const size_t g0 = lo_of(q), g1 = hi_of(q);
+      for (int k = 1; k < W; k++) {
+        int j = r + k; if (j >= W) j -= W;
+        size_t lo = (size_t)j * a.chunk + g0;
+        size_t cnt = clip_count(lo, (size_t)j * a.chunk + g1, a.n);
+        if (cnt) copy_tile<uint8_t, false>(reinterpret_cast<uint8_t*>(c.arena[j] + half_off) + lo, src + lo, cnt);
+      }
+      {
+        size_t lo = (size_t)r * a.chunk + g0;
+        size_t cnt = clip_count(lo, (size_t)r * a.chunk + g1, a.n);
+        if (cnt) multicast_tile<false>(mc + lo, reinterpret_cast<const uint4*>(src + lo), cnt / 16);
+      }
+      __syncthreads();
+      if (t < W && t != r) {
+        // one fence covers both flags of this peer
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        st_relaxed_sys(reinterpret_cast<uint32_t*>(c.arena[t] + kOffPipeA) + (size_t)blockIdx.x * 8 + r, a.pipe_base + q + 1);
+        st_relaxed_sys(reinterpret_cast<uint32_t*>(c.arena[t] + kOffPipeB) + (size_t)blockIdx.x * 8 + r, a.pipe_base + q + 1);
+      }
+    }
+    return;
+  }
+  uint8_t* out = static_cast<uint8_t*>(a.out);
+  const uint32_t* fA = reinterpret_cast<const uint32_t*>(c.arena[r] + kOffPipeA) + (size_t)blockIdx.x * 8 + root;
+  for (int q = 0; q <= R; q++) {
+    if (q < R) {
+      if (!block_wait_one(fA, a.pipe_base + q + 1, c, root, 1)) return;
+      size_t lo = (size_t)r * a.chunk + lo_of(q);
+      size_t cnt = clip_count(lo, (size_t)r * a.chunk + hi_of(q), a.n);
+      if (cnt) multicast_tile<true>(mc + lo, reinterpret_cast<const uint4*>(mine + lo), cnt / 16);
+      round_signal(kOffPipeB, a.pipe_base + q + 1, c);
+    }
+    if (q >= 1) {
+      if (!round_wait(kOffPipeB, a.pipe_base + q, c, 2)) return;
+      const size_t g0 = lo_of(q - 1), g1 = hi_of(q - 1);
+      for (int j = 0; j < W; j++) {
+        size_t lo = (size_t)j * a.chunk + g0;
+        size_t cnt = clip_count(lo, (size_t)j * a.chunk + g1, a.n);
+        if (cnt) copy_tile<uint8_t, true>(out + lo, mine + lo, cnt);
+      }
+    }
   }
 }
 
 // barrier: arrive[] exchange only (the prologue publishes arrive = seq; wait for everyone at seq).
-__global__ void __launch_bounds__(32) k_barrier(CollArgs a) {
+__global__ void __launch_bounds__(32) k_barrier(const __grid_constant__ CollArgs a) {
   const DevComm& c = a.c;
   int t = threadIdx.x;
   if (t < c.world && t != c.rank) {
@@ -107,7 +183,7 @@ struct P2PArgs {
   uint32_t ncells;
 };
 
-__global__ void __launch_bounds__(kThreads) k_send(P2PArgs a) {
+__global__ void __launch_bounds__(kThreads) k_send(const __grid_constant__ P2PArgs a) {
   const DevComm& c = a.c;
   const int r = c.rank, d = a.peer;
   const size_t cb = c.p2p_cell_bytes;
@@ -130,7 +206,7 @@ __global__ void __launch_bounds__(kThreads) k_send(P2PArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads) k_recv(P2PArgs a) {
+__global__ void __launch_bounds__(kThreads) k_recv(const __grid_constant__ P2PArgs a) {
   const DevComm& c = a.c;
   const int r = c.rank, s = a.peer;
   const size_t cb = c.p2p_cell_bytes;

@@ -1,10 +1,14 @@
 // Collective kernels over peer-mapped arenas (hand-written for sm_100a; no NCCL on this path).
 //
 // Partitioning: a piece of n elements is cut into `world` rank chunks of
-// `chunk` elements; each chunk is cut into per-block tiles of `tile` elements.  Block b of
-// every rank works on tile b of every chunk, so cross-rank dependencies are only between
-// blocks with the same index and are carried by the flag pair [block][src] in the signal pad.
-// No intra-grid synchronisation exists, so blocks need not be co-resident.
+// `chunk` elements; each chunk is cut into granules of `tile` elements.  Block b of every rank
+// works on granules b, b + grid, b + 2*grid, ... of every chunk (block-cyclic), so
+//   * cross-rank dependencies exist only between blocks with the same index and are carried by
+//     the flag pair [block][src] in the signal pad — no intra-grid synchronisation, blocks need
+//     not be co-resident;
+//   * at any time the whole grid touches one contiguous window of each chunk (grid * tile
+//     elements), which keeps DRAM pages and TLB entries hot on the side that serves peer /
+//     multimem reads, instead of `grid` streams spread over the whole message.
 //
 // Staging is double-buffered by sequence parity (a.seq & 1); coll_prologue() makes the reuse
 // safe for asymmetric ops as well.
@@ -22,78 +26,218 @@ __device__ __forceinline__ size_t clip_count(size_t lo, size_t hi, size_t n) {
   if (lo >= n) return 0;
   return (hi < n ? hi : n) - lo;
 }
+// granules of a chunk of `extent` elements owned by this block: [g0, g1) for g0 = first, first + step, ...
+#define B200C_FOR_GRANULES(g0, g1, a, extent)                                                                 \
+  for (size_t g0 = (size_t)blockIdx.x * (a).tile, g1 = g0 + (a).tile < (extent) ? g0 + (a).tile : (extent); \
+       g0 < (extent);                                                                                          \
+       g0 += (size_t)gridDim.x * (a).tile, g1 = g0 + (a).tile < (extent) ? g0 + (a).tile : (extent))
 
 // ---------------------------------------------------------------------------------------------
 // one-shot allreduce: push the whole buffer to every peer, reduce locally.  One flag round.
 // staging slot s (n_pad elements of TW) on rank j holds rank s's data.
 // ---------------------------------------------------------------------------------------------
 template <typename TI, typename TW, int OP>
-__global__ void __launch_bounds__(kThreads, 2) k_allreduce_oneshot(CollArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) k_allreduce_oneshot(const __grid_constant__ CollArgs a) {
   const DevComm& c = a.c;
   const int r = c.rank, W = c.world;
   if (!coll_prologue(a)) return;
-  const size_t t0 = (size_t)blockIdx.x * a.tile;
-  const size_t cnt = clip_count(t0, t0 + a.tile, a.n);
   const TI* in = static_cast<const TI*>(a.in);
   TI* out = static_cast<TI*>(a.out);
   const size_t slot_bytes = a.chunk * sizeof(TW);  // chunk == padded n for one-shot
-  if (cnt) {
+  B200C_FOR_GRANULES(t0, t1, a, a.n) {
     for (int k = 1; k < W; k++) {
       int j = r + k; if (j >= W) j -= W;
-      TW* dst = staging_ptr<TW>(c, j, a.seq, (size_t)r * slot_bytes) + t0;
-      move_tile<TI, TW, false>(dst, in + t0, cnt);
+      move_tile<TI, TW, false>(staging_ptr<TW>(c, j, a.seq, (size_t)r * slot_bytes) + t0, in + t0, t1 - t0);
     }
   }
   block_signal_all(kOffFlagA, a.seq, c);
   if (!block_wait_all(my_flags(kOffFlagA, c), a.seq, c, 1)) return;
   check_signature(a);
-  if (cnt) {
-    reduce_tile<TI, TW, OP>(a, staging_ptr<TW>(c, r, a.seq, 0) + t0, a.chunk, r, in + t0, nullptr, out + t0, cnt);
+  B200C_FOR_GRANULES(t0, t1, a, a.n) {
+    reduce_tile<TI, TW, OP>(a, staging_ptr<TW>(c, r, a.seq, 0) + t0, a.chunk, r, in + t0, nullptr, out + t0, t1 - t0);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
+// LL one-shot allreduce for small messages (latency-bound): every 32-bit payload word travels in
+// one naturally aligned 8-byte store {data, flag} (single-copy atomic), so there is no separate
+// flag round and no release fence between data and flag — the receiver polls the slot itself.
+// flag = a.ll_seq (per-communicator LL op counter, never 0); the region is double-buffered by
+// ll_seq & 1.  Reuse is safe without the arrive rule: a peer can only write LL op k+2 after it
+// finished op k+1, which needed this rank's op k+1 data, which this rank sends after its op k
+// kernel (which read every slot) has completed.
+// Layout on rank j: half h, source s, vector i  ->  4 consecutive u64 {word, flag}.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_ll2(void* p, uint32_t d0, uint32_t d1, uint32_t flag) {
+  asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"((unsigned long long)d0 | ((unsigned long long)flag << 32)),
+               "l"((unsigned long long)d1 | ((unsigned long long)flag << 32))
+               : "memory");
+}
+__device__ __forceinline__ void ld_ll2(const void* p, unsigned long long& a0, unsigned long long& a1) {
+  asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "l"(p) : "memory");
+}
+__device__ __forceinline__ char* ll_slot(const DevComm& c, int on_rank, uint32_t ll_seq, int src) {
+  return c.arena[on_rank] + c.off_ll + ((size_t)(ll_seq & 1) * kMaxRanks + src) * c.ll_words * 8;
+}
+
+template <typename T, int OP, int WT>
+__device__ __forceinline__ void ll_allreduce_body(const CollArgs& a) {
+  using A = typename Traits<T>::A;
+  constexpr int V = 16 / sizeof(T);
+  const DevComm& c = a.c;
+  const int r = c.rank;
+  const int W = WT > 0 ? WT : c.world;
+  const T* in = static_cast<const T*>(a.in);
+  T* out = static_cast<T*>(a.out);
+  const size_t nv = (a.n + V - 1) / V;  // 16-byte vectors, the last one possibly partial
+  const bool vec_ok = aligned16(in) && aligned16(out);
+  const uint32_t flag = a.ll_seq;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e0 = i * V;
+    const bool full = vec_ok && e0 + V <= a.n;
+    Pack16<T> mine;
+    if (full) {
+      mine.u = *reinterpret_cast<const uint4*>(in + e0);
+    } else {
+      mine.u = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int e = 0; e < V; e++)
+        if (e0 + e < a.n) mine.e[e] = in[e0 + e];
+    }
+    for (int k = 1; k < W; k++) {
+      int j = r + k; if (j >= W) j -= W;
+      char* dst = ll_slot(c, j, flag, r) + i * 32;
+      st_ll2(dst, mine.u.x, mine.u.y, flag);
+      st_ll2(dst + 16, mine.u.z, mine.u.w, flag);
+    }
+    uint4 raw[WT > 0 ? WT : kMaxRanks];
+    bool ok = true;
+#pragma unroll
+    for (int s = 0; s < (WT > 0 ? WT : kMaxRanks); s++) {
+      if (s >= W || s == r) continue;
+      const char* src = ll_slot(c, r, flag, s) + i * 32;
+      unsigned long long q0, q1, q2, q3;
+      unsigned spins = 0;
+      unsigned long long t_start = 0;
+      for (;;) {
+        ld_ll2(src, q0, q1);
+        ld_ll2(src + 16, q2, q3);
+        if ((uint32_t)(q0 >> 32) == flag && (uint32_t)(q1 >> 32) == flag && (uint32_t)(q2 >> 32) == flag && (uint32_t)(q3 >> 32) == flag) break;
+        if ((++spins & 0x3ff) == 0) {
+          if (t_start == 0) t_start = globaltimer_ns();
+          // a peer that entered the same op with different arguments will never fill this slot: compare signatures
+          const unsigned long long* sl = reinterpret_cast<const unsigned long long*>(c.arena[r] + kOffOpSig) + (a.seq & 1) * 8 + s;
+          unsigned long long sv;
+          asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(sv) : "l"(sl) : "memory");
+          if ((uint32_t)(sv >> 32) == a.seq && (uint32_t)sv != a.sig) {
+            if (c.status->error == 0) { c.status->err_a = (uint32_t)sv; c.status->err_b = a.sig; }
+            record_error(c.status, B200C_EMISMATCH, a.seq, s, 5);
+            c.status->abort_flag = 1;
+            ok = false; break;
+          }
+          if (c.status->abort_flag) { record_error(c.status, B200C_EABORTED, a.seq, s, 5); ok = false; break; }
+          if (globaltimer_ns() - t_start > c.timeout_ns) { record_error(c.status, B200C_ETIMEOUT, a.seq, s, 5); ok = false; break; }
+        }
+      }
+      raw[s] = make_uint4((uint32_t)q0, (uint32_t)q1, (uint32_t)q2, (uint32_t)q3);
+    }
+    if (!ok) return;
+    A acc[V];
+#pragma unroll
+    for (int s = 0; s < (WT > 0 ? WT : kMaxRanks); s++) {
+      if (s >= W) continue;
+      Pack16<T> p;
+      p.u = (s == r) ? mine.u : raw[s];
+#pragma unroll
+      for (int e = 0; e < V; e++) {
+        A x = Traits<T>::to_acc(p.e[e]);
+        acc[e] = (s == 0) ? x : Red<OP, A>::f(acc[e], x);
+      }
+    }
+    Pack16<T> res;
+#pragma unroll
+    for (int e = 0; e < V; e++) {
+      A v = acc[e];
+      if (a.has_scale) v = apply_scale<A>(v, a.scale, W);
+      res.e[e] = Traits<T>::from_acc(v);
+    }
+    if (full) {
+      *reinterpret_cast<uint4*>(out + e0) = res.u;
+    } else {
+#pragma unroll
+      for (int e = 0; e < V; e++)
+        if (e0 + e < a.n) out[e0 + e] = res.e[e];
+    }
+  }
+}
+
+constexpr int kLLThreads = 256;
+template <typename T, int OP>
+__global__ void __launch_bounds__(kLLThreads) k_allreduce_ll(const __grid_constant__ CollArgs a) {
+  const DevComm& c = a.c;
+  const int t = threadIdx.x;
+  // announce (seq, signature) first — a plain store, no fence — so a peer that entered this op with
+  // different arguments is diagnosed instead of both sides timing out
+  if (blockIdx.x == 0 && t < c.world && t != c.rank) {
+    unsigned long long* sig = reinterpret_cast<unsigned long long*>(c.arena[t] + kOffOpSig) + (a.seq & 1) * 8 + c.rank;
+    unsigned long long tagged = ((unsigned long long)a.seq << 32) | a.sig;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(sig), "l"(tagged) : "memory");
+  }
+  switch (c.world) {
+    case 2: ll_allreduce_body<T, OP, 2>(a); break;
+    case 4: ll_allreduce_body<T, OP, 4>(a); break;
+    case 8: ll_allreduce_body<T, OP, 8>(a); break;
+    default: ll_allreduce_body<T, OP, 0>(a); break;
+  }
+  // arrival (the op after this one may start: arrive rule) goes last so that the fence of the release
+  // does not sit in front of the data stores
+  if (blockIdx.x == 0 && t < c.world && t != c.rank)
+    st_release_sys(reinterpret_cast<uint32_t*>(c.arena[t] + kOffArrive) + c.rank, a.seq);
+}
+
+// ---------------------------------------------------------------------------------------------
 // two-shot allreduce.
-//   A: push tile b of chunk j to rank j's staging slot [r]          (NVLink egress, stores)
+//   A: push granule of chunk j to rank j's staging slot [r]          (NVLink egress, stores)
 //   B: reduce the W contributions of the own chunk in rank order; result -> own slot [r] + out
-//   C: pull every other rank's reduced tile                          (NVLink ingress, loads)
+//   C: pull every other rank's reduced granule                       (NVLink ingress, loads)
 // ---------------------------------------------------------------------------------------------
 template <typename TI, typename TW, int OP>
-__global__ void __launch_bounds__(kThreads, 2) k_allreduce_twoshot(CollArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) k_allreduce_twoshot(const __grid_constant__ CollArgs a) {
   const DevComm& c = a.c;
   const int r = c.rank, W = c.world;
   if (!coll_prologue(a)) return;
-  const size_t t0 = (size_t)blockIdx.x * a.tile;
-  const size_t t1 = (t0 + a.tile < a.chunk) ? t0 + a.tile : a.chunk;
   const TI* in = static_cast<const TI*>(a.in);
   TI* out = static_cast<TI*>(a.out);
   const size_t slot_bytes = a.chunk * sizeof(TW);
   // ---- A
-  for (int k = 1; k < W; k++) {
-    int j = r + k; if (j >= W) j -= W;
-    size_t lo = (size_t)j * a.chunk + t0;
-    size_t cnt = t0 < t1 ? clip_count(lo, (size_t)j * a.chunk + t1, a.n) : 0;
-    if (cnt) move_tile<TI, TW, false>(staging_ptr<TW>(c, j, a.seq, (size_t)r * slot_bytes) + t0, in + lo, cnt);
+  B200C_FOR_GRANULES(t0, t1, a, a.chunk) {
+    for (int k = 1; k < W; k++) {
+      int j = r + k; if (j >= W) j -= W;
+      size_t lo = (size_t)j * a.chunk + t0;
+      size_t cnt = clip_count(lo, (size_t)j * a.chunk + t1, a.n);
+      if (cnt) move_tile<TI, TW, false>(staging_ptr<TW>(c, j, a.seq, (size_t)r * slot_bytes) + t0, in + lo, cnt);
+    }
   }
   block_signal_all(kOffFlagA, a.seq, c);
   if (!block_wait_all(my_flags(kOffFlagA, c), a.seq, c, 1)) return;
   check_signature(a);
   // ---- B
-  {
+  B200C_FOR_GRANULES(t0, t1, a, a.chunk) {
     size_t lo = (size_t)r * a.chunk + t0;
-    size_t cnt = t0 < t1 ? clip_count(lo, (size_t)r * a.chunk + t1, a.n) : 0;
-    if (cnt) {
+    size_t cnt = clip_count(lo, (size_t)r * a.chunk + t1, a.n);
+    if (cnt)
       reduce_tile<TI, TW, OP>(a, staging_ptr<TW>(c, r, a.seq, 0) + t0, a.chunk, r, in + lo, staging_ptr<TW>(c, r, a.seq, (size_t)r * slot_bytes) + t0, out + lo, cnt);
-    }
   }
   block_signal_all(kOffFlagB, a.seq, c);
   if (!block_wait_all(my_flags(kOffFlagB, c), a.seq, c, 2)) return;
   // ---- C
-  for (int k = 1; k < W; k++) {
-    int j = r + k; if (j >= W) j -= W;
-    size_t lo = (size_t)j * a.chunk + t0;
-    size_t cnt = t0 < t1 ? clip_count(lo, (size_t)j * a.chunk + t1, a.n) : 0;
-    if (cnt) move_tile<TW, TI, true>(out + lo, staging_ptr<TW>(c, j, a.seq, (size_t)j * slot_bytes) + t0, cnt);
+  B200C_FOR_GRANULES(t0, t1, a, a.chunk) {
+    for (int k = 1; k < W; k++) {
+      int j = r + k; if (j >= W) j -= W;
+      size_t lo = (size_t)j * a.chunk + t0;
+      size_t cnt = clip_count(lo, (size_t)j * a.chunk + t1, a.n);
+      if (cnt) move_tile<TW, TI, true>(out + lo, staging_ptr<TW>(c, j, a.seq, (size_t)j * slot_bytes) + t0, cnt);
+    }
   }
 }
 
@@ -103,45 +247,43 @@ __global__ void __launch_bounds__(kThreads, 2) k_allreduce_twoshot(CollArgs a) {
 // Both are phases A+B of two-shot with full-size chunks.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int OP>
-__global__ void __launch_bounds__(kThreads, 2) k_reducescatter(CollArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) k_reducescatter(const __grid_constant__ CollArgs a) {
   const DevComm& c = a.c;
   const int r = c.rank, W = c.world;
   if (!coll_prologue(a)) return;
-  const size_t t0 = (size_t)blockIdx.x * a.tile;
-  const size_t cnt = clip_count(t0, t0 + a.tile, a.n);
   const size_t slot_bytes = a.chunk * sizeof(T);
-  if (cnt) {
+  B200C_FOR_GRANULES(t0, t1, a, a.n) {
     for (int k = 1; k < W; k++) {
       int j = r + k; if (j >= W) j -= W;
-      copy_tile<T, false>(staging_ptr<T>(c, j, a.seq, (size_t)r * slot_bytes) + t0, static_cast<const T*>(a.in_ptrs[j]) + t0, cnt);
+      copy_tile<T, false>(staging_ptr<T>(c, j, a.seq, (size_t)r * slot_bytes) + t0, static_cast<const T*>(a.in_ptrs[j]) + t0, t1 - t0);
     }
   }
   block_signal_all(kOffFlagA, a.seq, c);
   if (!block_wait_all(my_flags(kOffFlagA, c), a.seq, c, 1)) return;
   check_signature(a);
-  if (cnt) {
-    reduce_tile<T, T, OP>(a, staging_ptr<T>(c, r, a.seq, 0) + t0, a.chunk, r, static_cast<const T*>(a.in_ptrs[r]) + t0, nullptr, static_cast<T*>(a.out) + t0, cnt);
+  B200C_FOR_GRANULES(t0, t1, a, a.n) {
+    reduce_tile<T, T, OP>(a, staging_ptr<T>(c, r, a.seq, 0) + t0, a.chunk, r, static_cast<const T*>(a.in_ptrs[r]) + t0, nullptr, static_cast<T*>(a.out) + t0, t1 - t0);
   }
 }
 
 template <typename T, int OP>
-__global__ void __launch_bounds__(kThreads, 2) k_reduce(CollArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) k_reduce(const __grid_constant__ CollArgs a) {
   const DevComm& c = a.c;
   const int r = c.rank, root = a.root;
   if (!coll_prologue(a)) return;
-  const size_t t0 = (size_t)blockIdx.x * a.tile;
-  const size_t cnt = clip_count(t0, t0 + a.tile, a.n);
   const size_t slot_bytes = a.chunk * sizeof(T);
   if (r != root) {
-    if (cnt) copy_tile<T, false>(staging_ptr<T>(c, root, a.seq, (size_t)r * slot_bytes) + t0, static_cast<const T*>(a.in) + t0, cnt);
+    B200C_FOR_GRANULES(t0, t1, a, a.n) {
+      copy_tile<T, false>(staging_ptr<T>(c, root, a.seq, (size_t)r * slot_bytes) + t0, static_cast<const T*>(a.in) + t0, t1 - t0);
+    }
     block_signal_one(kOffFlagA, a.seq, c, root);
     // wait for root's release: completion of any rank then implies every rank has arrived
     block_wait_one(my_flags(kOffFlagB, c) + root, a.seq, c, root, 2);
   } else {
     if (!block_wait_all(my_flags(kOffFlagA, c), a.seq, c, 1)) return;
     check_signature(a);
-    if (cnt) {
-      reduce_tile<T, T, OP>(a, staging_ptr<T>(c, r, a.seq, 0) + t0, a.chunk, r, static_cast<const T*>(a.in) + t0, nullptr, static_cast<T*>(a.out) + t0, cnt);
+    B200C_FOR_GRANULES(t0, t1, a, a.n) {
+      reduce_tile<T, T, OP>(a, staging_ptr<T>(c, r, a.seq, 0) + t0, a.chunk, r, static_cast<const T*>(a.in) + t0, nullptr, static_cast<T*>(a.out) + t0, t1 - t0);
     }
     block_signal_all(kOffFlagB, a.seq, c);
   }
@@ -182,199 +324,169 @@ __device__ __forceinline__ void multimem_st16(void* p, uint4 v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// in-switch reduce of nv 16-byte vectors at multicast address `mc`, broadcast back in place
+template <typename TW>
+__device__ __forceinline__ void nvls_reduce_bcast(char* mc, size_t nv, const CollArgs& a) {
+  constexpr int V = 16 / sizeof(TW);
+  size_t i = threadIdx.x;
+  for (; i + (kUnroll - 1) * kThreads < nv; i += kUnroll * kThreads) {
+    uint4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) v[u] = Multimem<TW>::ld_reduce(mc + (i + u * kThreads) * 16);
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      if (a.has_scale) {
+        Pack16<TW> p; p.u = v[u];
+#pragma unroll
+        for (int e = 0; e < V; e++) p.e[e] = Traits<TW>::from_acc(Traits<TW>::to_acc(p.e[e]) * a.scale);
+        v[u] = p.u;
+      }
+      multimem_st16(mc + (i + u * kThreads) * 16, v[u]);
+    }
+  }
+  for (; i < nv; i += kThreads) {
+    uint4 v = Multimem<TW>::ld_reduce(mc + i * 16);
+    if (a.has_scale) {
+      Pack16<TW> p; p.u = v;
+#pragma unroll
+      for (int e = 0; e < V; e++) p.e[e] = Traits<TW>::from_acc(Traits<TW>::to_acc(p.e[e]) * a.scale);
+      v = p.u;
+    }
+    multimem_st16(mc + i * 16, v);
+  }
+}
+// user tensor -> staging for the granule [g0, g1) of every rank chunk (zero-pad the last vector so the
+// switch reduces defined values)
 template <typename TI, typename TW>
-__global__ void __launch_bounds__(kThreads, 2) k_allreduce_nvls(CollArgs a) {
+__device__ __forceinline__ void nvls_stage_in(const CollArgs& a, TW* mine, const TI* in, size_t g0, size_t g1) {
+  constexpr int V = 16 / sizeof(TW);
+  const int W = a.c.world;
+  for (int j = 0; j < W; j++) {
+    size_t lo = (size_t)j * a.chunk + g0, hi = (size_t)j * a.chunk + g1;
+    size_t cnt = clip_count(lo, hi, a.n);
+    if (cnt) move_tile<TI, TW, false>(mine + lo, in + lo, cnt);
+    size_t end = lo + cnt, padded = (end + V - 1) / V * V;
+    if (cnt && padded > end && padded <= hi) {
+      TW z = Traits<TW>::from_acc((typename Traits<TW>::A)0);
+      for (size_t k = end + threadIdx.x; k < padded; k += kThreads) mine[k] = z;
+    }
+  }
+}
+template <typename TI, typename TW>
+__device__ __forceinline__ void nvls_stage_out(const CollArgs& a, const TW* mine, TI* out, size_t g0, size_t g1) {
+  const int W = a.c.world;
+  for (int j = 0; j < W; j++) {
+    size_t lo = (size_t)j * a.chunk + g0;
+    size_t cnt = clip_count(lo, (size_t)j * a.chunk + g1, a.n);
+    if (cnt) move_tile<TW, TI, true>(out + lo, mine + lo, cnt);
+  }
+}
+
+template <typename TI, typename TW>
+__global__ void __launch_bounds__(kThreads, 2) k_allreduce_nvls(const __grid_constant__ CollArgs a) {
   const DevComm& c = a.c;
-  const int r = c.rank, W = c.world;
+  const int r = c.rank;
   if (!coll_prologue(a)) return;
   constexpr int V = 16 / sizeof(TW);
-  const size_t t0 = (size_t)blockIdx.x * a.tile;
-  const size_t t1 = (t0 + a.tile < a.chunk) ? t0 + a.tile : a.chunk;
   const TI* in = static_cast<const TI*>(a.in);
   TI* out = static_cast<TI*>(a.out);
   // byte offset (inside the arena) of element 0 of the buffer the switch works on
   const size_t base_off = a.symmetric ? a.sym_off : c.off_staging + (size_t)(a.seq & 1) * c.staging_bytes;
   TW* mine = reinterpret_cast<TW*>(c.arena[r] + base_off);
-  // ---- A: stage in (zero-pad the last vector so the switch reduces defined values)
-  if (!a.symmetric && t0 < t1) {
-    for (int j = 0; j < W; j++) {
-      size_t lo = (size_t)j * a.chunk + t0, hi = (size_t)j * a.chunk + t1;
-      size_t cnt = clip_count(lo, hi, a.n);
-      if (cnt) move_tile<TI, TW, false>(mine + lo, in + lo, cnt);
-      size_t end = lo + cnt, padded = (end + V - 1) / V * V;
-      if (cnt && padded > end && padded <= hi) {
-        TW z = Traits<TW>::from_acc((typename Traits<TW>::A)0);
-        for (size_t k = end + threadIdx.x; k < padded; k += kThreads) mine[k] = z;
-      }
-    }
+  // ---- A: stage in
+  if (!a.symmetric) {
+    B200C_FOR_GRANULES(g0, g1, a, a.chunk) nvls_stage_in<TI, TW>(a, mine, in, g0, g1);
   }
   block_signal_all(kOffFlagA, a.seq, c);
   if (!block_wait_all(my_flags(kOffFlagA, c), a.seq, c, 1)) return;
   check_signature(a);
-  // ---- B: in-switch reduce of the own chunk's tile, broadcast back in place
-  if (t0 < t1) {
-    size_t lo = (size_t)r * a.chunk + t0;
-    size_t cnt = clip_count(lo, (size_t)r * a.chunk + t1, a.n);
-    size_t nv = (cnt + V - 1) / V;
-    char* mc = c.mc_arena + base_off + lo * sizeof(TW);
-    size_t i = threadIdx.x;
-    for (; i + (kUnroll - 1) * kThreads < nv; i += kUnroll * kThreads) {
-      uint4 v[kUnroll];
-#pragma unroll
-      for (int u = 0; u < kUnroll; u++) v[u] = Multimem<TW>::ld_reduce(mc + (i + u * kThreads) * 16);
-#pragma unroll
-      for (int u = 0; u < kUnroll; u++) {
-        if (a.has_scale) {
-          Pack16<TW> p; p.u = v[u];
-#pragma unroll
-          for (int e = 0; e < V; e++) p.e[e] = Traits<TW>::from_acc(Traits<TW>::to_acc(p.e[e]) * a.scale);
-          v[u] = p.u;
-        }
-        multimem_st16(mc + (i + u * kThreads) * 16, v[u]);
-      }
-    }
-    for (; i < nv; i += kThreads) {
-      uint4 v = Multimem<TW>::ld_reduce(mc + i * 16);
-      if (a.has_scale) {
-        Pack16<TW> p; p.u = v;
-#pragma unroll
-        for (int e = 0; e < V; e++) p.e[e] = Traits<TW>::from_acc(Traits<TW>::to_acc(p.e[e]) * a.scale);
-        v = p.u;
-      }
-      multimem_st16(mc + i * 16, v);
-    }
+  // ---- B: in-switch reduce of the own chunk's granules, broadcast back in place
+  B200C_FOR_GRANULES(g0, g1, a, a.chunk) {
+    size_t lo = (size_t)r * a.chunk + g0;
+    size_t cnt = clip_count(lo, (size_t)r * a.chunk + g1, a.n);
+    if (cnt) nvls_reduce_bcast<TW>(c.mc_arena + base_off + lo * sizeof(TW), (cnt + V - 1) / V, a);
   }
   block_signal_all(kOffFlagB, a.seq, c);
   if (!block_wait_all(my_flags(kOffFlagB, c), a.seq, c, 2)) return;
   // ---- C: stage out
-  if (!a.symmetric && t0 < t1) {
-    for (int j = 0; j < W; j++) {
-      size_t lo = (size_t)j * a.chunk + t0;
-      size_t cnt = clip_count(lo, (size_t)j * a.chunk + t1, a.n);
-      if (cnt) move_tile<TW, TI, true>(out + lo, mine + lo, cnt);
-    }
+  if (!a.symmetric) {
+    B200C_FOR_GRANULES(g0, g1, a, a.chunk) nvls_stage_out<TI, TW>(a, mine, out, g0, g1);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pipelined staged NVLS allreduce (large plain tensors).  The CTA is split into three warp-
-// specialised roles that run concurrently on sub-tiles of the CTA's slab:
-//   IN  (192 threads): user tensor -> staging (every chunk's slice of sub-tile k), then raises
-//                      pipeA[block][rank] = base+k+1 on every rank (own pad included);
-//   RED (128 threads): waits pipeA from all W ranks, multimem.ld_reduce + multimem.st of the OWN
-//                      chunk's slice of sub-tile k, then raises pipeB the same way;
-//   OUT (192 threads): waits pipeB from all W ranks, staging -> user tensor.
-// The local HBM copies of sub-tiles k+1 / k-1 therefore overlap the switch traffic of sub-tile k,
-// instead of three back-to-back phases as in k_allreduce_nvls.  Roles talk only through the flags
-// (global memory) and synchronise internally with named barriers.
+// Round-pipelined staged NVLS allreduce (large plain tensors).  Same data flow as k_allreduce_nvls,
+// but the three stages are synchronised per ROUND (one granule of every chunk per block) instead of
+// per phase, and software-pipelined inside each block:
+//
+//     in(q+1) -> signalA(q+1) -> waitA(q) -> switch(q) -> signalB(q) -> waitB(q-1) -> out(q-1)
+//
+// so every wait has a full stage of local work in front of it, and — because a block only ever
+// depends on the same-index block of its peers, never on the rest of its own grid — blocks drift out
+// of phase as soon as the switch becomes the bottleneck: while some blocks queue on the switch the
+// others run their local HBM copies.  (The plain kernel keeps the whole grid in lock step: all copy
+// in, then all reduce, then all copy out — the link idles during both copies.)
+// Round flags live in pipeA / pipeB [block][src]; the value of round q is pipe_base + q + 1, and the
+// host advances pipe_base by the number of rounds of every such op.
 // ---------------------------------------------------------------------------------------------
-constexpr int kPipeIn = 192, kPipeRed = 128, kPipeOut = 192;
-static_assert(kPipeIn + kPipeRed + kPipeOut == kThreads, "roles must cover the CTA");
+__device__ __forceinline__ void round_signal(size_t flag_off, uint32_t v, const DevComm& c) {
+  __syncthreads();
+  int t = threadIdx.x;
+  if (t < c.world && t != c.rank) {
+    uint32_t* f = reinterpret_cast<uint32_t*>(c.arena[t] + flag_off) + (size_t)blockIdx.x * 8 + c.rank;
+    st_release_sys(f, v);
+  }
+}
+__device__ __forceinline__ bool round_wait(size_t flag_off, uint32_t v, const DevComm& c, int phase) {
+  const uint32_t* f = reinterpret_cast<const uint32_t*>(c.arena[c.rank] + flag_off) + (size_t)blockIdx.x * 8;
+  int ok = 1;
+  int t = threadIdx.x;
+  if (t < c.world && t != c.rank) ok = wait_flag(f + t, v, c, t, phase);
+  return __syncthreads_and(ok) != 0;
+}
 
 template <typename TI, typename TW>
-__global__ void __launch_bounds__(kThreads, 2) k_allreduce_nvls_pipe(CollArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) k_allreduce_nvls_rounds(const __grid_constant__ CollArgs a) {
   const DevComm& c = a.c;
-  const int r = c.rank, W = c.world;
+  const int r = c.rank;
   if (!coll_prologue(a)) return;
   check_signature(a);
-  __shared__ int s_fail;
-  if (threadIdx.x == 0) s_fail = 0;
-  __syncthreads();
   constexpr int V = 16 / sizeof(TW);
-  const size_t t0 = (size_t)blockIdx.x * a.tile;
-  const size_t t1 = (t0 + a.tile < a.chunk) ? t0 + a.tile : a.chunk;
-  if (t0 >= t1) return;
-  const int K = (int)((t1 - t0 + a.sub - 1) / a.sub);
   const TI* in = static_cast<const TI*>(a.in);
   TI* out = static_cast<TI*>(a.out);
   const size_t base_off = c.off_staging + (size_t)(a.seq & 1) * c.staging_bytes;
   TW* mine = reinterpret_cast<TW*>(c.arena[r] + base_off);
-  const size_t flag_idx = (size_t)blockIdx.x * 8;
-  const uint32_t* myA = reinterpret_cast<const uint32_t*>(c.arena[r] + kOffPipeA) + flag_idx;
-  const uint32_t* myB = reinterpret_cast<const uint32_t*>(c.arena[r] + kOffPipeB) + flag_idx;
-  const int tid = threadIdx.x;
-
-  if (tid < kPipeIn) {
-    // ------------------------------------------------------------------ IN
-    const int t = tid;
-    for (int k = 0; k < K; k++) {
-      const size_t s0 = t0 + (size_t)k * a.sub;
-      const size_t s1 = (s0 + a.sub < t1) ? s0 + a.sub : t1;
-      for (int j = 0; j < W; j++) {
-        size_t lo = (size_t)j * a.chunk + s0, hi = (size_t)j * a.chunk + s1;
-        size_t cnt = clip_count(lo, hi, a.n);
-        if (cnt) move_tile<TI, TW, false>(mine + lo, in + lo, cnt, t, kPipeIn);
-        size_t end = lo + cnt, padded = (end + V - 1) / V * V;
-        if (cnt && padded > end && padded <= hi) {
-          TW z = Traits<TW>::from_acc((typename Traits<TW>::A)0);
-          for (size_t q = end + t; q < padded; q += kPipeIn) mine[q] = z;
-        }
-      }
-      role_sync(1, kPipeIn);
-      if (t < W) st_release_sys(reinterpret_cast<uint32_t*>(c.arena[t] + kOffPipeA) + flag_idx + r, a.pipe_base + k + 1);
+  const size_t first = (size_t)blockIdx.x * a.tile, step = (size_t)gridDim.x * a.tile;
+  if (first >= a.chunk) return;
+  const int R = (int)((a.chunk - first + step - 1) / step);
+  auto lo_of = [&](int q) { return first + (size_t)q * step; };
+  auto hi_of = [&](int q) { size_t h = first + (size_t)q * step + a.tile; return h < a.chunk ? h : a.chunk; };
+  nvls_stage_in<TI, TW>(a, mine, in, lo_of(0), hi_of(0));
+  round_signal(kOffPipeA, a.pipe_base + 1, c);
+  for (int q = 0; q < R; q++) {
+    if (q + 1 < R) {
+      nvls_stage_in<TI, TW>(a, mine, in, lo_of(q + 1), hi_of(q + 1));
+      round_signal(kOffPipeA, a.pipe_base + q + 2, c);
     }
-  } else if (tid < kPipeIn + kPipeRed) {
-    // ------------------------------------------------------------------ RED
-    const int t = tid - kPipeIn;
-    for (int k = 0; k < K; k++) {
-      if (t < W && !wait_flag(myA + t, a.pipe_base + k + 1, c, t, 1)) s_fail = 1;
-      role_sync(2, kPipeRed);
-      if (s_fail) return;
-      const size_t s0 = t0 + (size_t)k * a.sub;
-      const size_t s1 = (s0 + a.sub < t1) ? s0 + a.sub : t1;
-      size_t lo = (size_t)r * a.chunk + s0;
-      size_t cnt = clip_count(lo, (size_t)r * a.chunk + s1, a.n);
-      size_t nv = (cnt + V - 1) / V;
-      char* mc = c.mc_arena + base_off + lo * sizeof(TW);
-      size_t i = t;
-      for (; i + (size_t)(kUnroll - 1) * kPipeRed < nv; i += (size_t)kUnroll * kPipeRed) {
-        uint4 v[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; u++) v[u] = Multimem<TW>::ld_reduce(mc + (i + (size_t)u * kPipeRed) * 16);
-#pragma unroll
-        for (int u = 0; u < kUnroll; u++) {
-          if (a.has_scale) {
-            Pack16<TW> p; p.u = v[u];
-#pragma unroll
-            for (int e = 0; e < V; e++) p.e[e] = Traits<TW>::from_acc(Traits<TW>::to_acc(p.e[e]) * a.scale);
-            v[u] = p.u;
-          }
-          multimem_st16(mc + (i + (size_t)u * kPipeRed) * 16, v[u]);
-        }
-      }
-      for (; i < nv; i += kPipeRed) {
-        uint4 v = Multimem<TW>::ld_reduce(mc + i * 16);
-        if (a.has_scale) {
-          Pack16<TW> p; p.u = v;
-#pragma unroll
-          for (int e = 0; e < V; e++) p.e[e] = Traits<TW>::from_acc(Traits<TW>::to_acc(p.e[e]) * a.scale);
-          v = p.u;
-        }
-        multimem_st16(mc + i * 16, v);
-      }
-      role_sync(2, kPipeRed);
-      if (t < W) st_release_sys(reinterpret_cast<uint32_t*>(c.arena[t] + kOffPipeB) + flag_idx + r, a.pipe_base + k + 1);
+    if (!round_wait(kOffPipeA, a.pipe_base + q + 1, c, 1)) return;
+    {
+      size_t lo = (size_t)r * a.chunk + lo_of(q);
+      size_t cnt = clip_count(lo, (size_t)r * a.chunk + hi_of(q), a.n);
+      if (cnt) nvls_reduce_bcast<TW>(c.mc_arena + base_off + lo * sizeof(TW), (cnt + V - 1) / V, a);
     }
-  } else {
-    // ------------------------------------------------------------------ OUT
-    const int t = tid - kPipeIn - kPipeRed;
-    for (int k = 0; k < K; k++) {
-      if (t < W && !wait_flag(myB + t, a.pipe_base + k + 1, c, t, 2)) s_fail = 1;
-      role_sync(3, kPipeOut);
-      if (s_fail) return;
-      const size_t s0 = t0 + (size_t)k * a.sub;
-      const size_t s1 = (s0 + a.sub < t1) ? s0 + a.sub : t1;
-      for (int j = 0; j < W; j++) {
-        size_t lo = (size_t)j * a.chunk + s0;
-        size_t cnt = clip_count(lo, (size_t)j * a.chunk + s1, a.n);
-        if (cnt) move_tile<TW, TI, true>(out + lo, mine + lo, cnt, t, kPipeOut);
-      }
+    round_signal(kOffPipeB, a.pipe_base + q + 1, c);
+    if (q >= 1) {
+      if (!round_wait(kOffPipeB, a.pipe_base + q, c, 2)) return;
+      nvls_stage_out<TI, TW>(a, mine, out, lo_of(q - 1), hi_of(q - 1));
     }
   }
+  if (!round_wait(kOffPipeB, a.pipe_base + R, c, 2)) return;
+  nvls_stage_out<TI, TW>(a, mine, out, lo_of(R - 1), hi_of(R - 1));
 }
 
 // world == 1: no peers, only the wire rounding and the scale remain (the DDP hook at N = 1).
-// Grid-stride over 16-byte vectors, four loads in flight per thread; HBM-bound (read n, write n).
+// Grid-stride over 16-byte vectors, four loads in flight per thread; the host sizes the grid to the
+// resident capacity (no second, partial wave); HBM-bound (read n, write n).
 template <typename TI, typename TW>
 __device__ __forceinline__ TI local_scale_one(TI x, const CollArgs& a) {
   using A = typename Traits<TW>::A;
@@ -384,7 +496,7 @@ __device__ __forceinline__ TI local_scale_one(TI x, const CollArgs& a) {
 }
 
 template <typename TI, typename TW>
-__global__ void __launch_bounds__(kThreads) k_local_scale(CollArgs a) {
+__global__ void __launch_bounds__(kThreads) k_local_scale(const __grid_constant__ CollArgs a) {
   constexpr int VI = 16 / sizeof(TI);
   const TI* in = static_cast<const TI*>(a.in);
   TI* out = static_cast<TI*>(a.out);

@@ -59,6 +59,8 @@ struct DevComm {
   size_t off_p2p;           // arena offset of the p2p rings [8 src][cells][cell_bytes]
   size_t p2p_cell_bytes;
   int p2p_cells;
+  size_t off_ll;            // arena offset of the LL (packed data+flag) region: [2 halves][8 src][ll_words] u64
+  size_t ll_words;          // 32-bit payload words per source slot (one u64 {data, flag} each)
 };
 
 struct CollArgs {
@@ -67,14 +69,17 @@ struct CollArgs {
   void* out;
   size_t n;        // elements in this piece
   size_t chunk;    // elements per rank chunk (multiple of the 16-byte vector width)
-  size_t tile;     // elements per block tile (multiple of the 16-byte vector width)
+  size_t tile;     // elements per granule (multiple of the 16-byte vector width).  Block b owns granules
+                   // b, b + grid, b + 2*grid, ... of every rank chunk (block-cyclic: at any time the grid
+                   // touches one contiguous window of each chunk, which keeps DRAM pages / TLB entries hot on
+                   // the serving side of peer and multimem reads)
   uint32_t seq;    // this op's sequence number (>= 1)
   uint32_t sig;    // op signature for mismatch detection
   int root;
   int has_scale;
   float scale;
-  size_t sub;      // pipelined kernels: elements per sub-tile (multiple of the vector width)
-  uint32_t pipe_base;  // pipelined kernels: flag value of sub-tile k is pipe_base + k + 1
+  uint32_t pipe_base;  // round-pipelined kernels: flag value of round q is pipe_base + q + 1
+  uint32_t ll_seq;     // LL kernels: per-communicator LL op counter (flag value; half = ll_seq & 1)
   int symmetric;   // NVLS: in/out already live at the same offset of the symmetric region
   size_t sym_off;  // arena offset of that buffer
   const void* in_ptrs[kMaxRanks];
@@ -107,6 +112,17 @@ __device__ __forceinline__ uint4 ld_bypass16(const void* p) {
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(p)
                : "memory");
+  return v;
+}
+// predicated form: a single @p LDG, no branch — keeps a compile-time-indexed batch of loads in registers
+// when one of them (the rank's own slot) has to be skipped at run time
+__device__ __forceinline__ uint4 ld_bypass16_if(const void* p, bool cond) {
+  uint4 v = make_uint4(0, 0, 0, 0);
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\t@q ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+      : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w)
+      : "l"(p), "r"((int)cond)
+      : "memory");
   return v;
 }
 template <int N> struct RawInt;
@@ -376,21 +392,18 @@ __device__ __forceinline__ void move_tile(TD* dst, const TS* src, size_t n, int 
 //   s == own_idx which is `own` (TI, user memory, rounded through TW so every rank's contribution is
 //   treated alike).
 //   dst_w (TW, may be nullptr): result for peers to pull.  dst_i (TI, may be nullptr): user output.
-template <typename TI, typename TW, int OP>
-__device__ __forceinline__ void reduce_tile(const CollArgs& a, const TW* src0, size_t src_stride, int own_idx,
-                                            const TI* own, TW* dst_w, TI* dst_i, size_t n) {
+// WT > 0: the world size is a compile-time constant, so the W in-flight vectors live in registers
+// (a runtime-indexed array would be demoted to local memory); WT == 0 handles the odd world sizes
+// (3, 5, 6, 7) by folding each contribution as it is loaded.
+template <typename TI, typename TW, int OP, int WT>
+__device__ __forceinline__ void reduce_vectors(const CollArgs& a, const TW* src0, size_t src_stride, int own_idx,
+                                               const TI* own, TW* dst_w, TI* dst_i, size_t nv) {
   using A = typename Traits<TW>::A;
   constexpr int V = 16 / sizeof(TW);
   constexpr int VI = 16 / sizeof(TI);
-  const int W = a.c.world;
-  const int t = threadIdx.x;
-  static_assert(sizeof(TI) >= sizeof(TW), "wire type must not be wider than the buffer type");
-  bool vec = aligned16(own) && (dst_i == nullptr || aligned16(dst_i));
-  size_t nv = vec ? n / V : 0;
-  for (size_t i = t; i < nv; i += kThreads) {
+  const int W = WT > 0 ? WT : a.c.world;
+  for (size_t i = threadIdx.x; i < nv; i += kThreads) {
     A acc[V];
-    // issue every source's load first (memory-level parallelism), then fold in rank order
-    Pack16<TW> p[kMaxRanks];
     TI ownv[V];
     {
       const uint4* o = reinterpret_cast<const uint4*>(own + i * V);
@@ -402,18 +415,42 @@ __device__ __forceinline__ void reduce_tile(const CollArgs& a, const TW* src0, s
         for (int e = 0; e < VI; e++) ownv[q * VI + e] = po.e[e];
       }
     }
+    if (WT > 0) {
+      // loads are issued in batches of up to four sources (memory-level parallelism without exceeding
+      // the 64-register budget of two 512-thread CTAs per SM), then folded in rank order
+      constexpr int B = WT < 4 ? (WT > 0 ? WT : 1) : 4;
 #pragma unroll
-    for (int s = 0; s < kMaxRanks; s++)
-      if (s < W && s != own_idx) p[s].u = ld_bypass16(reinterpret_cast<const uint4*>(src0 + (size_t)s * src_stride + i * V));
+      for (int s0 = 0; s0 < WT; s0 += B) {
+        uint4 raw[B];
 #pragma unroll
-    for (int s = 0; s < kMaxRanks; s++) {
-      if (s >= W) break;
+        for (int k = 0; k < B; k++)
+          raw[k] = ld_bypass16_if(reinterpret_cast<const uint4*>(src0 + (size_t)(s0 + k) * src_stride + i * V), s0 + k != own_idx);
 #pragma unroll
-      for (int e = 0; e < V; e++) {
-        A x;
-        if (s == own_idx) x = Traits<TW>::to_acc(Traits<TW>::from_acc((A)Traits<TI>::to_acc(ownv[e])));
-        else x = Traits<TW>::to_acc(p[s].e[e]);
-        acc[e] = (s == 0) ? x : Red<OP, A>::f(acc[e], x);
+        for (int k = 0; k < B; k++) {
+          const int s = s0 + k;
+          Pack16<TW> p;
+          p.u = raw[k];
+#pragma unroll
+          for (int e = 0; e < V; e++) {
+            A x;
+            if (s == own_idx) x = Traits<TW>::to_acc(Traits<TW>::from_acc((A)Traits<TI>::to_acc(ownv[e])));
+            else x = Traits<TW>::to_acc(p.e[e]);
+            acc[e] = (s == 0) ? x : Red<OP, A>::f(acc[e], x);
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int s = 0; s < W; s++) {
+        Pack16<TW> p;
+        p.u = ld_bypass16_if(reinterpret_cast<const uint4*>(src0 + (size_t)s * src_stride + i * V), s != own_idx);
+#pragma unroll
+        for (int e = 0; e < V; e++) {
+          A x;
+          if (s == own_idx) x = Traits<TW>::to_acc(Traits<TW>::from_acc((A)Traits<TI>::to_acc(ownv[e])));
+          else x = Traits<TW>::to_acc(p.e[e]);
+          acc[e] = (s == 0) ? x : Red<OP, A>::f(acc[e], x);
+        }
       }
     }
     Pack16<TW> r;
@@ -434,6 +471,24 @@ __device__ __forceinline__ void reduce_tile(const CollArgs& a, const TW* src0, s
         d[q] = po.u;
       }
     }
+  }
+}
+
+template <typename TI, typename TW, int OP>
+__device__ __forceinline__ void reduce_tile(const CollArgs& a, const TW* src0, size_t src_stride, int own_idx,
+                                            const TI* own, TW* dst_w, TI* dst_i, size_t n) {
+  using A = typename Traits<TW>::A;
+  constexpr int V = 16 / sizeof(TW);
+  const int W = a.c.world;
+  const int t = threadIdx.x;
+  static_assert(sizeof(TI) >= sizeof(TW), "wire type must not be wider than the buffer type");
+  bool vec = aligned16(own) && (dst_i == nullptr || aligned16(dst_i));
+  size_t nv = vec ? n / V : 0;
+  switch (W) {
+    case 2: reduce_vectors<TI, TW, OP, 2>(a, src0, src_stride, own_idx, own, dst_w, dst_i, nv); break;
+    case 4: reduce_vectors<TI, TW, OP, 4>(a, src0, src_stride, own_idx, own, dst_w, dst_i, nv); break;
+    case 8: reduce_vectors<TI, TW, OP, 8>(a, src0, src_stride, own_idx, own, dst_w, dst_i, nv); break;
+    default: reduce_vectors<TI, TW, OP, 0>(a, src0, src_stride, own_idx, own, dst_w, dst_i, nv); break;
   }
   for (size_t k = nv * V + t; k < n; k += kThreads) {
     A acc = A();

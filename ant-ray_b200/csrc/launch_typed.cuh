@@ -5,7 +5,7 @@
 
 namespace b200c {
 
-enum Kind { KIND_ONESHOT = 0, KIND_TWOSHOT = 1, KIND_REDUCESCATTER = 2, KIND_REDUCE = 3 };
+enum Kind { KIND_ONESHOT = 0, KIND_TWOSHOT = 1, KIND_REDUCESCATTER = 2, KIND_REDUCE = 3, KIND_LL = 4 };
 
 template <typename T, int OP>
 static int launch_kind(int kind, const CollArgs& a, int grid, cudaStream_t s) {
@@ -14,6 +14,7 @@ static int launch_kind(int kind, const CollArgs& a, int grid, cudaStream_t s) {
     case KIND_TWOSHOT: k_allreduce_twoshot<T, T, OP><<<grid, kThreads, 0, s>>>(a); break;
     case KIND_REDUCESCATTER: k_reducescatter<T, OP><<<grid, kThreads, 0, s>>>(a); break;
     case KIND_REDUCE: k_reduce<T, OP><<<grid, kThreads, 0, s>>>(a); break;
+    case KIND_LL: k_allreduce_ll<T, OP><<<grid, kLLThreads, 0, s>>>(a); break;
     default: return B200C_EINVAL;
   }
   return B200C_OK;

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define B200C_VERSION 100 /* 0.1.0 */
+#define B200C_VERSION 200 /* 0.2.0 */
 #define B200C_MAX_RANKS 8 /* one NVSwitch domain */
 
 /* ncclDataType_t numbering (reference: nccl_util.py:30-71 maps numpy/torch dtypes onto these). */
@@ -62,7 +62,8 @@ typedef enum {
   B200C_ALGO_ONESHOT = 1, /* every rank pushes its whole buffer to every peer, reduces locally */
   B200C_ALGO_TWOSHOT = 2, /* push reduce-scatter + pull all-gather over peer memory */
   B200C_ALGO_NVLS = 3,    /* multimem.ld_reduce / multimem.st on the NVSwitch multicast object */
-  B200C_ALGO_NVLS_PIPE = 4 /* same, staged copies overlapped with the switch traffic (warp-specialised pipeline) */
+  B200C_ALGO_NVLS_PIPE = 4,/* same, staged copies overlapped with the switch traffic (per-round flags, software-pipelined blocks) */
+  B200C_ALGO_LL = 5        /* packed {data, flag} 8-byte stores, one NVLink hop, no fence: small messages */
 } b200c_algo_t;
 
 typedef enum {
@@ -93,8 +94,13 @@ typedef struct {
   uint32_t max_blocks;         /* upper bound on CTAs per collective kernel (<= 2048) */
   uint64_t oneshot_max_bytes;  /* AUTO: message <= this -> one-shot */
   uint64_t nvls_min_bytes;     /* AUTO: message >= this and multicast bound -> NVLS */
-  uint64_t nvls_pipe_min_bytes;/* AUTO: staged NVLS pieces >= this use the pipelined kernel (0 = never) */
+  uint64_t nvls_pipe_min_bytes;/* AUTO: staged NVLS pieces >= this use the round-pipelined kernel (0 = never) */
   uint64_t timeout_ms;         /* device-side bounded spin; 0 = default (600 s; NCCL's watchdog default is of that order) */
+  uint64_t granule_bytes;      /* block-cyclic granule of the large-message kernels (multiple of 16 KiB; 0 = 32 KiB) */
+  uint64_t ll_max_bytes;       /* AUTO: same-type allreduce <= this goes by the LL kernel; also sizes the LL region (0 = no LL) */
+  uint64_t bcast_rounds_min_bytes; /* broadcast >= this uses scatter + multicast-allgather rounds (0 = never) */
+  uint32_t nvls_blocks;        /* CTAs of the NVLS kernels (0 = max_blocks) */
+  uint32_t reserved0;
 } b200c_config_t;
 
 typedef struct {

@@ -41,7 +41,7 @@ def test_library_has_no_libcuda_link_dependency():
 
 def test_load_and_host_side_calls():
     lib = N.load()
-    assert lib.b200c_version() == 100
+    assert lib.b200c_version() == 200
     assert [lib.b200c_dtype_size(d) for d in range(10)] == [1, 1, 4, 4, 8, 8, 2, 4, 8, 2]
     assert lib.b200c_dtype_size(99) == 0
     cfg = N.default_config()
