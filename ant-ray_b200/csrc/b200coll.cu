@@ -545,6 +545,16 @@ extern "C" int b200c_debug_fill_flags(b200c_comm_t* c, uint32_t value) {
   cudaError_t e = cudaMemcpy(c->arena[c->rank], host, kPadUsed, cudaMemcpyHostToDevice);
   delete[] host;
   if (e != cudaSuccess) return fail(B200C_ECUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
+  // LL slots are matched by equality, not by >=: pre-stamp both halves with the flag of the NEXT LL op
+  // (payload 0) so that exactly one LL launch can run without its peers
+  size_t ll_u64 = 2 * (size_t)kMaxRanks * c->ll_words;
+  if (ll_u64) {
+    unsigned long long* h = new unsigned long long[ll_u64];
+    for (size_t i = 0; i < ll_u64; i++) h[i] = (unsigned long long)(c->ll_seq + 1) << 32;
+    e = cudaMemcpy(c->arena[c->rank] + c->off_ll, h, ll_u64 * 8, cudaMemcpyHostToDevice);
+    delete[] h;
+    if (e != cudaSuccess) return fail(B200C_ECUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
+  }
   return B200C_OK;
 }
 

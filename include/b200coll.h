@@ -224,7 +224,8 @@ int b200c_barrier(b200c_comm_t* comm, b200c_stream_t stream);
  * wait of every later op is already satisfied, so ONE rank's kernel can run without its peers —
  * which is what Nsight Compute's kernel replay needs (it re-runs a kernel in isolation, so a kernel
  * that waits for a concurrently running peer kernel would never finish).  Results are garbage;
- * memory traffic and instruction mix are those of the real run.  Never call it on a live group. */
+ * memory traffic and instruction mix are those of the real run.  The LL region is stamped with the
+ * flag of the next LL op (one LL launch per call).  Never call it on a live group. */
 int b200c_debug_fill_flags(b200c_comm_t* comm, uint32_t value);
 
 /* Launch statistics (bench.py's gpu_launches claim). */

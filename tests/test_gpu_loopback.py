@@ -60,6 +60,60 @@ def test_allreduce_ops(world, dtype, opname, algo):
         _run_allreduce(world, dtype, n, opname, algo)
 
 
+LL_SIZES = [1, 3, 10, 257, 4000]   # 4000 x 8-byte elements = 32,000 bytes: just under the 32 KiB LL capacity
+
+
+@pytest.mark.parametrize("dtype", INT_DTYPES + FLOAT_DTYPES)
+def test_allreduce_ll_all_dtypes(world, dtype):
+    """LL path (packed data+flag stores, no flag round): same rank-order fold, so bit-exact too."""
+    for n in LL_SIZES:
+        _run_allreduce(world, dtype, n, "sum", N.ALGO_LL)
+    _run_allreduce(world, dtype, 100, "sum", N.ALGO_LL, inplace=False)
+
+
+@pytest.mark.parametrize("opname", ["prod", "max", "min", "avg"])
+@pytest.mark.parametrize("dtype", [torch.int32, torch.int64, torch.uint8, torch.float32, torch.bfloat16, torch.float64])
+def test_allreduce_ll_ops(world, dtype, opname):
+    for n in (7, 3001):
+        _run_allreduce(world, dtype, n, opname, N.ALGO_LL)
+
+
+def test_allreduce_ll_limits_and_auto(world):
+    """AUTO picks LL up to ll_max_bytes; asking for LL beyond the region's capacity is refused, not truncated."""
+    _run_allreduce(world, torch.float32, 8192, "sum", N.ALGO_AUTO)       # exactly 32 KiB -> LL
+    _run_allreduce(world, torch.float32, 8193, "sum", N.ALGO_AUTO)       # one element more -> one-shot
+    x = torch.ones(8193, device="cuda")
+    with pytest.raises(N.B200CollError) as ei:
+        world.comms[0].allreduce(x.data_ptr(), x.data_ptr(), 8193, N.FLOAT32, N.SUM, N.ALGO_LL)
+    assert ei.value.status == N.EUNSUPPORTED
+    # the refused call must not have consumed a sequence number: the next op still lines up with the peers
+    _run_allreduce(world, torch.int32, 100, "sum", N.ALGO_LL)
+    with pytest.raises(N.B200CollError):
+        world.comms[0].allreduce_scaled(x.data_ptr(), x.data_ptr(), 100, N.FLOAT32, N.BFLOAT16, 0.5, N.ALGO_LL)
+    _run_allreduce(world, torch.int32, 100, "sum", N.ALGO_TWOSHOT)
+
+
+def test_allreduce_ll_unaligned_and_scaled(world):
+    W, n = world.world_size, 1001
+    ins = [make_input(torch.float32, n + 1, r) for r in range(W)]
+    cur = [t.cuda() for t in ins]
+    world.run(lambda r, c: c.allreduce(cur[r][1:].data_ptr(), cur[r][1:].data_ptr(), n, N.FLOAT32, N.SUM, N.ALGO_LL))
+    torch.cuda.synchronize()
+    world.check()
+    want = O.allreduce([t[1:] for t in ins])
+    for r in range(W):
+        assert_equal_bits(cur[r][1:], want, "LL unaligned")
+        assert cur[r][0].item() == ins[r][0].item()
+    # fused mean with an fp32 wire takes LL under AUTO for small buckets (the RLlib-sized case)
+    dev = [t[:n].contiguous().cuda() for t in ins]
+    world.run(lambda r, c: c.allreduce_scaled(dev[r].data_ptr(), dev[r].data_ptr(), n, N.FLOAT32, N.FLOAT32, 1.0 / W, N.ALGO_AUTO))
+    torch.cuda.synchronize()
+    world.check()
+    want = O.allreduce_scaled([t[:n] for t in ins], None, 1.0 / W)
+    for r in range(W):
+        assert_equal_bits(dev[r], want, "LL fused mean fp32 wire")
+
+
 def test_allreduce_out_of_place_and_auto(world):
     for n in (5, 70_000):
         _run_allreduce(world, torch.float32, n, "sum", N.ALGO_AUTO, inplace=False)
@@ -184,13 +238,15 @@ def test_send_recv(world):
 
 
 def test_barrier_and_back_to_back(world):
-    """200 small collectives in a row exercise the double-buffered staging and the flag epochs."""
+    """200 small collectives in a row exercise the double-buffered staging, the LL region halves and the
+    flag epochs (LL skips the prologue wait, so it is interleaved with the staged algorithms on purpose)."""
     W, n = world.world_size, 300
     ins = [make_input(torch.int32, n, r) for r in range(W)]
     dev = [t.cuda() for t in ins]
     acc = [t.clone() for t in ins]
+    cycle = [N.ALGO_TWOSHOT, N.ALGO_LL, N.ALGO_LL, N.ALGO_ONESHOT, N.ALGO_LL]
     for it in range(200):
-        world.run(lambda r, c: c.allreduce(dev[r].data_ptr(), dev[r].data_ptr(), n, N.INT32, N.SUM, N.ALGO_ONESHOT if it % 2 else N.ALGO_TWOSHOT))
+        world.run(lambda r, c: c.allreduce(dev[r].data_ptr(), dev[r].data_ptr(), n, N.INT32, N.SUM, cycle[it % len(cycle)]))
         s = O.allreduce(acc)
         acc = [s.clone() for _ in range(W)]
         if it % 50 == 0:
@@ -199,6 +255,76 @@ def test_barrier_and_back_to_back(world):
     world.check()
     for r in range(W):
         assert_equal_bits(dev[r], acc[r], "after 200 allreduces")
+
+
+@pytest.mark.parametrize("W", [2, 4])
+def test_block_cyclic_granules(W):
+    """Few blocks + the smallest granule: every block loops over several granules of every chunk (the
+    large-message layout), with ragged tails, for every kernel that uses it."""
+    from ant_ray_b200.loopback import LoopbackWorld
+
+    w = LoopbackWorld(W, device=0, key=f"lb-gran{W}", staging_bytes=4 << 20, max_blocks=3, granule_bytes=16384, timeout_ms=20000)
+    try:
+        n = 300_007
+        for dtype, algo in ((torch.float32, N.ALGO_TWOSHOT), (torch.int32, N.ALGO_ONESHOT), (torch.bfloat16, N.ALGO_TWOSHOT)):
+            _run_allreduce(w, dtype, n, "sum", algo)
+        ins = [make_input(torch.float32, n, r) for r in range(W)]
+        dev = [t.cuda() for t in ins]
+        w.run(lambda r, c: c.allreduce_scaled(dev[r].data_ptr(), dev[r].data_ptr(), n, N.FLOAT32, N.BFLOAT16, 1.0 / W, N.ALGO_TWOSHOT))
+        torch.cuda.synchronize()
+        w.check()
+        want = O.allreduce_scaled(ins, torch.bfloat16, 1.0 / W)
+        for r in range(W):
+            assert_equal_bits(dev[r], want, "granules: fused mean")
+        m = 120_001
+        lists = [[make_input(torch.int32, m, r * 16 + j) for j in range(W)] for r in range(W)]
+        devl = [[t.cuda() for t in row] for row in lists]
+        outs = [torch.empty(m, dtype=torch.int32, device="cuda") for _ in range(W)]
+        w.run(lambda r, c: c.reducescatter([t.data_ptr() for t in devl[r]], outs[r].data_ptr(), m, N.INT32, N.SUM))
+        gouts = [[torch.zeros(m, dtype=torch.int32, device="cuda") for _ in range(W)] for _ in range(W)]
+        w.run(lambda r, c: c.allgather(devl[r][0].data_ptr(), [t.data_ptr() for t in gouts[r]], m, N.INT32))
+        torch.cuda.synchronize()
+        w.check()
+        want = O.reducescatter(lists)
+        for r in range(W):
+            assert_equal_bits(outs[r], want[r], "granules: reducescatter")
+            for j in range(W):
+                assert_equal_bits(gouts[r][j], lists[j][0], "granules: allgather")
+        for root in (0, W - 1):
+            dev = [t.cuda() for t in ins]
+            w.run(lambda r, c: c.broadcast(dev[r].data_ptr(), n, N.FLOAT32, root))
+            torch.cuda.synchronize()
+            for r in range(W):
+                assert_equal_bits(dev[r], ins[root], "granules: broadcast")
+            dev = [t.cuda() for t in ins]
+            w.run(lambda r, c: c.reduce(dev[r].data_ptr(), dev[r].data_ptr(), n, N.FLOAT32, N.SUM, root))
+            torch.cuda.synchronize()
+            w.check()
+            for r in range(W):
+                assert_equal_bits(dev[r], O.reduce(ins) if r == root else ins[r], "granules: reduce")
+    finally:
+        w.destroy()
+
+
+def test_ll_mismatch_is_detected_not_hung():
+    """LL has no flag round to compare arguments on: a peer that entered the op with a different count is
+    diagnosed from the poll loop (signature slot), not by waiting out the timeout."""
+    import time
+
+    from ant_ray_b200.loopback import LoopbackWorld
+
+    w = LoopbackWorld(2, device=0, key="lb-ll-mismatch", staging_bytes=1 << 20, timeout_ms=30000)
+    try:
+        x = [torch.ones(64, device="cuda"), torch.ones(128, device="cuda")]
+        t0 = time.time()
+        w.run(lambda r, c: c.allreduce(x[r].data_ptr(), x[r].data_ptr(), x[r].numel(), N.FLOAT32, N.SUM, N.ALGO_LL))
+        torch.cuda.synchronize()
+        assert time.time() - t0 < 10, "mismatch must not wait for the 30 s device timeout"
+        with pytest.raises(N.B200CollError) as ei:
+            w.check()
+        assert ei.value.status in (N.EMISMATCH, N.EABORTED)
+    finally:
+        w.destroy()
 
 
 def test_mismatch_is_detected_not_hung():

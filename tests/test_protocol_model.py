@@ -12,8 +12,9 @@ asserts the two safety properties the kernels rely on:
 
 Modelled: W ranks, B blocks per kernel, kernels of one rank strictly ordered (one stream), blocks of
 a kernel in arbitrary order, cross-rank flags monotonically increasing, ops = two-shot allreduce,
-one-shot allreduce, staged NVLS allreduce, broadcast (root runs ahead without waiting for anyone), reduce (non-roots wait
-for the root's release), barrier.  Each rank's block executes the same step list the CUDA code
+one-shot allreduce, staged NVLS allreduce (phase-synchronised and round-pipelined), broadcast (root runs
+ahead without waiting for anyone; unicast and scatter + multicast-allgather rounds), reduce (non-roots wait
+for the root's release), barrier, and the LL (packed data+flag, no prologue wait) small-message allreduce.  Each rank's block executes the same step list the CUDA code
 does.  The last test removes the `arrive` wait and shows that the checker then finds a violation —
 i.e. the rule is necessary and the model can see that.
 """
@@ -27,11 +28,15 @@ class Violation(AssertionError):
 
 
 class World:
+    ROUNDS = 3   # rounds per block of the round-pipelined kernels
+
     def __init__(self, W, B, ops, use_arrive_rule=True):
         self.W, self.B, self.ops, self.rule = W, B, ops, use_arrive_rule
         self.arrive = [[0] * W for _ in range(W)]                       # arrive[rank][src]
         self.flagA = [[[0] * W for _ in range(B)] for _ in range(W)]    # flagA[rank][block][src]
         self.flagB = [[[0] * W for _ in range(B)] for _ in range(W)]
+        self.pipeA = [[[0] * W for _ in range(B)] for _ in range(W)]    # per-round flags of the pipelined kernels
+        self.pipeB = [[[0] * W for _ in range(B)] for _ in range(W)]
         self.content = {}     # region -> seq of the data it holds
         self.pending = {}     # region -> set of (rank, block) that still have to read that data
         self.op_idx = [0] * W                                            # kernel each rank is in
@@ -45,7 +50,20 @@ class World:
         kind, root = self.ops[k]
         q, W, h = k + 1, self.W, (k + 1) & 1
         peers = [j for j in range(W) if j != r]
+        everyone = list(range(W))
         st = []
+        R = self.ROUNDS
+        # host-side counters every rank advances identically: round-flag epoch and LL op number
+        e = R * sum(1 for kk, _ in self.ops[:k] if kk in ("nvls_rounds", "bcast_rounds"))
+        ll_no = 1 + sum(1 for kk, _ in self.ops[:k] if kk == "ll")
+        if kind == "ll":
+            # no prologue wait; data and flag travel together; arrive is published last
+            lh = ("ll", ll_no & 1)
+            st += [("write", (j, lh, r, b), ("ll", ll_no), {(j, b)}) for j in peers]
+            st += [("ll_read", (r, lh, s, b), ("ll", ll_no)) for s in peers]
+            if b == 0:
+                st += [("set_arrive", j, q) for j in peers]
+            return st
         if kind == "barrier":
             if b == 0:
                 st += [("set_arrive", j, q) for j in peers] + [("wait_arrive", j, q) for j in peers]
@@ -74,6 +92,41 @@ class World:
             st += [("write", (j, h, ("out", r), b), q, {(j, b)}) for j in everyone]          #    ... and multicasts the result back
             st += [("sigB", j, q) for j in peers] + [("waitB", j, q) for j in peers]
             st += [("read", (r, h, ("out", j), b), q) for j in everyone]                     # C: stage out
+        elif kind == "nvls_rounds":
+            # software pipeline of k_allreduce_nvls_rounds: in(q+1) | waitA(q) switch(q) sigB(q) | waitB(q-1) out(q-1)
+            def stage_in(x):
+                return [("write", (r, h, ("in", x), b), q, {(j, b) for j in everyone})] + [("sigPA", j, e + x + 1) for j in peers]
+
+            def stage_out(x):
+                return [("waitPB", j, e + x + 1) for j in peers] + [("read", (r, h, ("out", j, x), b), q) for j in everyone]
+
+            st += stage_in(0)
+            for x in range(R):
+                if x + 1 < R:
+                    st += stage_in(x + 1)
+                st += [("waitPA", j, e + x + 1) for j in peers]
+                st += [("read", (j, h, ("in", x), b), q) for j in everyone]
+                st += [("write", (j, h, ("out", r, x), b), q, {(j, b)}) for j in everyone]
+                st += [("sigPB", j, e + x + 1) for j in peers]
+                if x >= 1:
+                    st += stage_out(x - 1)
+            st += stage_out(R - 1)
+        elif kind == "bcast_rounds":
+            others = [j for j in everyone if j != root]
+            if r == root:
+                for x in range(R):
+                    st += [("write", (j, h, ("sc", x), b), q, {(j, b)}) for j in peers]                 # unicast scatter
+                    st += [("write", (j, h, ("mc", r, x), b), q, {(j, b)}) for j in peers]              # own chunk multicast
+                    st += [("sigPA", j, e + x + 1) for j in peers] + [("sigPB", j, e + x + 1) for j in peers]
+            else:
+                for x in range(R + 1):
+                    if x < R:
+                        st += [("waitPA", root, e + x + 1), ("read", (r, h, ("sc", x), b), q)]
+                        st += [("write", (j, h, ("mc", r, x), b), q, ({(j, b)} if j in others and j != r else set())) for j in everyone if j != r]
+                        st += [("sigPB", j, e + x + 1) for j in peers]
+                    if x >= 1:
+                        st += [("waitPB", j, e + x) for j in peers]
+                        st += [("read", (r, h, ("mc", j, x - 1), b), q) for j in everyone if j != r]
         elif kind == "broadcast":
             if r == root:
                 st += [("write", (j, h, 0, b), q, {(j, b)}) for j in peers]                  # root pushes, waits for nobody
@@ -107,6 +160,12 @@ class World:
             return self.flagA[r][b][step[1]] >= step[2]
         if op == "waitB":
             return self.flagB[r][b][step[1]] >= step[2]
+        if op == "waitPA":
+            return self.pipeA[r][b][step[1]] >= step[2]
+        if op == "waitPB":
+            return self.pipeB[r][b][step[1]] >= step[2]
+        if op == "ll_read":  # the receiver polls the slot itself: ready once the flag of THIS op is there
+            return self.content.get(step[1]) == step[2]
         return True
 
     def step(self, r, b):
@@ -118,6 +177,12 @@ class World:
             self.flagA[s[1]][b][r] = s[2]
         elif op == "sigB":
             self.flagB[s[1]][b][r] = s[2]
+        elif op == "sigPA":
+            assert s[2] > self.pipeA[s[1]][b][r], "round flags must increase monotonically"
+            self.pipeA[s[1]][b][r] = s[2]
+        elif op == "sigPB":
+            assert s[2] > self.pipeB[s[1]][b][r], "round flags must increase monotonically"
+            self.pipeB[s[1]][b][r] = s[2]
         elif op == "write":
             region, q, readers = s[1], s[2], s[3]
             # Conservative aliasing: one-shot and two-shot lay slots and tiles out differently inside a
@@ -128,7 +193,7 @@ class World:
                     raise Violation(f"S1: rank {r} block {b} op {q} writes {region} while {sorted(self.pending[other])} "
                                     f"still have to read op {seq} data in {other} of the same staging half")
             self.content[region], self.pending[region] = q, set(readers)
-        elif op == "read":
+        elif op in ("read", "ll_read"):
             region, q = s[1], s[2]
             if self.content.get(region) != q:
                 raise Violation(f"S2: rank {r} block {b} op {q} reads {region} holding op {self.content.get(region)}")
@@ -160,7 +225,7 @@ class World:
 
 
 def random_ops(rng, W, n):
-    kinds = ["twoshot", "oneshot", "nvls", "broadcast", "reduce", "barrier"]
+    kinds = ["twoshot", "oneshot", "nvls", "nvls_rounds", "ll", "broadcast", "bcast_rounds", "reduce", "barrier"]
     return [(k, rng.randrange(W)) for k in (rng.choice(kinds) for _ in range(n))]
 
 
@@ -214,6 +279,18 @@ def test_mixed_algorithms_share_the_staging_safely():
     ops = [("twoshot", 0), ("broadcast", 1), ("oneshot", 0), ("reduce", 2), ("twoshot", 0), ("broadcast", 0), ("oneshot", 0)] * 3
     for slow in range(4):
         World(4, 2, ops).run(rng, lambda r, b: 0.02 if r == slow else 1.0)
+
+
+def test_ll_and_round_pipelined_kernels_between_asymmetric_ops():
+    """LL skips the prologue wait and the round kernels share one flag epoch: interleave them with
+    producer-only ops (a root that runs ahead) and a very slow / very fast rank."""
+    rng = random.Random(23)
+    ops = [("ll", 0), ("broadcast", 1), ("ll", 0), ("ll", 0), ("nvls_rounds", 0), ("bcast_rounds", 2), ("ll", 0),
+           ("bcast_rounds", 0), ("nvls_rounds", 0), ("twoshot", 0), ("ll", 0), ("reduce", 1), ("ll", 0)] * 2
+    for W, B in ((3, 2), (4, 1), (8, 1)):
+        for slow in range(min(W, 3)):
+            for weight in (0.02, 30.0):
+                World(W, B, ops).run(rng, lambda r, b: weight if r == slow else 1.0)
 
 
 # ---------------------------------------------------------------------------------------------
