@@ -204,9 +204,7 @@ class PeerMemoryComm:
     def destroy(self):
         if self.handle is not None:
             h, self.handle = self.handle, None
-            self.lib.b200c_comm_destroy(h)
-            if self.rank == 0:
-                rendezvous.cleanup_keys(self.store, self.key, self.world_size)
+            self.lib.b200c_comm_destroy(h)  # the rendezvous keys were already deleted when establish() finished
 
     def symmetric_tensor(self, shape, dtype, byte_offset: int = 0):
         """A torch tensor aliasing this rank's symmetric region at `byte_offset`.  The same offset
@@ -278,12 +276,21 @@ class PeerMemoryComm:
 
 
 def next_comm_key(group_name: str) -> str:
-    """Rendezvous key of the n-th incarnation of a group name in this process (groups may be
-    destroyed and re-created under the same name: single_node_cpu_tests/test_allreduce.py:37-59)."""
+    """Key of the n-th incarnation of a group name in this process.  Only for callers whose ranks are
+    all created and re-created in lock step inside one job (the gloo test oracle, bench.py); the
+    B200 group itself uses `group_key`, which carries no process-local state."""
     with _incarnations_lock:
         n = _incarnations.get(group_name, 0)
         _incarnations[group_name] = n + 1
     return f"b200coll/{group_name}/{n}"
+
+
+def group_key(group_name: str) -> str:
+    """Rendezvous prefix of a named group.  Incarnations are told apart by the random epoch rank 0
+    publishes at every creation (rendezvous._agree_on_epoch), not by a per-process counter, so groups
+    may be destroyed and re-created under the same name (single_node_cpu_tests/test_allreduce.py:37-59)
+    and a single restarted actor still meets its surviving peers."""
+    return f"b200coll/{group_name}"
 
 
 class B200Group:
@@ -299,7 +306,7 @@ class B200Group:
         self._store, self._device, self._config = store, device, config
         self._comm: Optional[PeerMemoryComm] = None
         self._destroyed = False
-        self._key = next_comm_key(group_name)
+        self._key = group_key(group_name)
 
     # -- BaseGroup surface ----------------------------------------------------------------------
     @property
@@ -323,6 +330,20 @@ class B200Group:
         if self._comm is not None:
             self._comm.destroy()
             self._comm = None
+
+    def check(self, synchronize: bool = False):
+        """Raise if a kernel of this group recorded a failure (peer timeout, abort, argument mismatch).
+        Collectives are asynchronous like NCCL's: a device-side failure is otherwise only seen by the
+        next call.  `synchronize=True` first waits for the work queued so far."""
+        if self._comm is None:
+            return
+        if synchronize:
+            import torch
+
+            torch.cuda.current_stream(self._comm.device).synchronize()
+            if self._comm._last_stream is not None:
+                self._comm._last_stream.synchronize()
+        self._comm.check()
 
     def comm(self, device: Optional[int] = None) -> PeerMemoryComm:
         """The lazily-created communicator (first op decides the device, like the reference's

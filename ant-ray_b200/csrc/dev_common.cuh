@@ -158,7 +158,11 @@ static __device__ __noinline__ bool wait_slow(const uint32_t* flag, uint32_t seq
     if ((int32_t)(ld_acquire_sys(flag) - seq) >= 0) return true;
     if ((++spins & 0xff) == 0) {
       if (st->abort_flag) { record_error(st, B200C_EABORTED, seq, peer, phase); return false; }
-      if (globaltimer_ns() - t0 > timeout_ns) { record_error(st, B200C_ETIMEOUT, seq, peer, phase); return false; }
+      if (globaltimer_ns() - t0 > timeout_ns) {
+        record_error(st, B200C_ETIMEOUT, seq, peer, phase);
+        st->abort_flag = 1;  // the op has failed: let this rank's other blocks (and queued kernels) stop waiting too
+        return false;
+      }
       __nanosleep(64);
     }
   }

@@ -30,7 +30,7 @@ _BUCKET = {torch.float32: N.FLOAT32, torch.bfloat16: N.BFLOAT16, torch.float16: 
 class B200GradState:
     """Hook state: the peer-memory communicator, the wire dtype and the communication stream."""
 
-    def __init__(self, comm: PeerMemoryComm, wire="bf16", algo: int = N.ALGO_AUTO, time_kernels: bool = False):
+    def __init__(self, comm: PeerMemoryComm, wire="fp32", algo: int = N.ALGO_AUTO, time_kernels: bool = False):
         if wire not in _WIRE:
             raise ValueError("wire must be one of fp32 / bf16 / fp16")
         self.comm = comm
@@ -75,7 +75,7 @@ def b200_allreduce_hook(state: B200GradState, bucket) -> torch.futures.Future[to
 
 
 def make_grad_state(world_size: Optional[int] = None, rank: Optional[int] = None, device: Optional[int] = None,
-                    wire="bf16", store=None, config=None, name: str = "ddp", **kw) -> B200GradState:
+                    wire="fp32", store=None, config=None, name: str = "ddp", **kw) -> B200GradState:
     """Build the communicator for the hook from the torch.distributed world (rank / world size and,
     by default, the default process group's store for the rendezvous)."""
     import torch.distributed as dist

@@ -4,9 +4,14 @@ Restates python/ray/experimental/gpu_object_manager/collective_tensor_transport.
 `TensorTransportManager` contract (tensor_transport_manager.py:14-151): metadata extraction,
 communicator lookup through the driver-side registry, and per-tensor send / recv through the
 collective API (`collective.send/recv`, reference :128-170).  Differences:
-  * `can_abort_transport()` is True: a peer-memory group can be aborted (every kernel wait is
-    bounded and polls the abort flag), so Ray need not kill the actors on a transfer error;
-  * `abort_transport` is implemented (the reference raises NotImplementedError).
+  * `abort_transport` is implemented (the reference raises NotImplementedError): it releases the
+    kernels of this actor that wait on the peer.  `can_abort_transport()` nevertheless stays False,
+    as in the reference's collective transport: an abort poisons the communicator (sticky abort
+    flag, recorded error, the two peers' ring positions no longer agree), so the group cannot carry
+    another transfer and Ray must treat the actors as lost, exactly as it does for NCCL;
+  * `recv_multiple_tensors` synchronises and checks the communicator before handing the tensors
+    to the consumer, so a transfer that failed on the device (peer death, timeout) raises instead of
+    returning uninitialised memory.
 It is still two-sided (`is_one_sided() == False`): the receiver posts a recv per tensor.
 """
 from dataclasses import dataclass, field
@@ -45,7 +50,7 @@ class B200TensorTransport:
 
     @staticmethod
     def can_abort_transport() -> bool:
-        return True
+        return False
 
     def actor_has_tensor_transport(self, actor) -> bool:
         return len(_xc.get_collective_groups([actor], backend=self._backend)) > 0
@@ -79,6 +84,10 @@ class B200TensorTransport:
         assert isinstance(communicator_metadata, CollectiveCommunicatorMetadata)
         for t in tensors:
             _col.recv(t, communicator_metadata.src_rank, communicator_metadata.communicator_name)
+        g = _col.get_group_handle(communicator_metadata.communicator_name)
+        check = getattr(g, "check", None)
+        if tensors and check is not None:
+            check(synchronize=True)  # the data must have landed, and landed intact, before the consumer sees it
 
     def send_multiple_tensors(self, tensors: list, tensor_transport_metadata: TensorTransportMetadata,
                               communicator_metadata: CollectiveCommunicatorMetadata):

@@ -178,15 +178,24 @@ _REQ = struct.Struct("<ii")  # (requester rank, kind) kind: 0 = arena export, 1 
 
 
 class FdServer:
-    """Serves this rank's exported fds to its peers.  One short-lived thread per group."""
+    """Serves this rank's exported fds to its peers.  One short-lived thread per group.
 
-    def __init__(self):
+    The socket lives in the abstract namespace (no filesystem permissions), so every request is
+    authenticated with SO_PEERCRED: the peer must run under this process's uid and — once the group's
+    pids are known (`allow`) — be one of the group's processes; the claimed rank must be in range and
+    each (rank, kind) is served once."""
+
+    def __init__(self, world: Optional[int] = None, rank: Optional[int] = None):
         self.sock = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
         self.address = "\0b200coll-" + uuid.uuid4().hex
         self.sock.bind(self.address)
         self.sock.listen(64)
         self.sock.settimeout(0.1)
+        self.world, self.rank = world, rank
         self.payloads = {}  # kind -> (bytes, fd)
+        self.allowed_pids = None  # rank -> pid, set by allow()
+        self.served = set()
+        self.rejected = 0
         self.lock = threading.Lock()
         self.stop = threading.Event()
         self.thread = threading.Thread(target=self._serve, name="b200coll-fd-server", daemon=True)
@@ -195,6 +204,37 @@ class FdServer:
     def offer(self, kind: int, data: bytes, fd: int):
         with self.lock:
             self.payloads[kind] = (data, fd)
+
+    def allow(self, pids):
+        """pids[r] = process id of rank r (as published through the store)."""
+        with self.lock:
+            self.allowed_pids = dict(enumerate(pids))
+
+    def _authorised(self, conn, rank: int, kind: int) -> bool:
+        try:
+            pid, uid, _gid = struct.unpack("3i", conn.getsockopt(socket.SOL_SOCKET, socket.SO_PEERCRED, struct.calcsize("3i")))
+        except OSError:
+            return False
+        if uid != os.getuid():
+            return False
+        if self.world is not None and not (0 <= rank < self.world and rank != self.rank):
+            return False
+        deadline = time.monotonic() + 60
+        while self.world is not None:  # group servers wait for the pid list; ad-hoc servers (tests) skip it
+            with self.lock:
+                allowed = self.allowed_pids
+            if allowed is not None:
+                if allowed.get(rank) != pid:
+                    return False
+                break
+            if time.monotonic() > deadline or self.stop.is_set():
+                return False
+            time.sleep(0.001)
+        with self.lock:
+            if (rank, kind) in self.served:
+                return False
+            self.served.add((rank, kind))
+        return True
 
     def _serve(self):
         while not self.stop.is_set():
@@ -214,7 +254,10 @@ class FdServer:
                     raw += part
                 if len(raw) != _REQ.size:
                     continue
-                _, kind = _REQ.unpack(raw)
+                rank, kind = _REQ.unpack(raw)
+                if not self._authorised(conn, rank, kind):
+                    self.rejected += 1
+                    continue
                 deadline = time.monotonic() + 60
                 while True:
                     with self.lock:
@@ -279,6 +322,53 @@ def _barrier(store: Store, prefix: str, tag: str, rank: int, world: int, timeout
     return [store.get(f"{prefix}/{tag}/{r}", timeout_s) for r in range(world)]
 
 
+def _proc_start_time(pid: int) -> Optional[str]:
+    """Kernel start time (clock ticks since boot) of a live process, None if there is no such process.
+    (pid, start time) never repeats on a box, unlike the pid alone."""
+    try:
+        with open(f"/proc/{pid}/stat", "rb") as f:
+            stat = f.read().decode(errors="replace")
+        return stat[stat.rindex(")") + 2:].split()[19]
+    except (OSError, ValueError, IndexError):
+        return None
+
+
+def _agree_on_epoch(store: Store, prefix: str, rank: int, timeout_s: float) -> str:
+    """Give this incarnation of the group a fresh key namespace.
+
+    Stores outlive processes (Ray's internal KV, a /dev/shm directory), so keys of an earlier incarnation
+    that crashed — or that was never destroyed — may still be there.  Rank 0 publishes a new random epoch
+    together with its (pid, start time); the other ranks accept an epoch only from a publisher that is
+    alive right now, so a dead incarnation's epoch is ignored until the live rank 0 overwrites it.  Every
+    other rendezvous key lives under the epoch; a successful rendezvous deletes all of them, the epoch
+    key included (see establish), so a finished incarnation leaves nothing a later one could pick up.
+    Nothing is derived from process-local counters: a single restarted actor agrees with its surviving
+    peers as soon as they re-create the group."""
+    key = f"{prefix}/epoch"
+    if rank == 0:
+        epoch = uuid.uuid4().hex
+        store.set(key, f"{epoch}:{os.getpid()}:{_proc_start_time(os.getpid())}".encode())
+        return epoch
+    trust = os.environ.get("B200COLL_TRUST_EPOCH") == "1"  # ranks in different pid namespaces cannot check liveness
+    deadline = time.monotonic() + timeout_s
+    while True:
+        try:
+            raw = store.get(key, min(0.25, max(0.01, deadline - time.monotonic())))
+            epoch, pid, started = raw.decode().split(":")
+            if trust or _proc_start_time(int(pid)) == started:
+                return epoch
+        except RendezvousTimeout:
+            pass
+        except ValueError:
+            pass  # a foreign or half-written value: wait for rank 0
+        if time.monotonic() > deadline:
+            raise RendezvousTimeout(f"no live rank 0 published an epoch for '{prefix}' within {timeout_s}s")
+        time.sleep(0.005)
+
+
+_TAGS = ("addr", "ipc", "imported", "mc_created", "mc_added", "mc_bound", "ready", "done")
+
+
 def establish(comm: int, store: Store, prefix: str, rank: int, world: int, share_mode: int,
               want_multicast: bool, timeout_s: float = 60.0) -> bool:
     """Drive a freshly created native communicator (`b200c_comm_create`) to the ready state.
@@ -296,11 +386,18 @@ def establish(comm: int, store: Store, prefix: str, rank: int, world: int, share
     server: Optional[FdServer] = None
     own_fd = exp.fd
     mc_fd_own = -1
+    base = prefix
+    epoch = None
+    ok_all = False
     try:
+        epoch = _agree_on_epoch(store, base, rank, timeout_s)
+        prefix = f"{base}/{epoch}"
         if share_mode == N.SHARE_VMM_FD:
-            server = FdServer()
+            server = FdServer(world, rank)
             server.offer(0, bytes(exp), own_fd)
-            addrs = _barrier(store, prefix, "addr", rank, world, timeout_s, server.address.encode())
+            hello = _barrier(store, prefix, "addr", rank, world, timeout_s, server.address.encode() + b"|" + str(os.getpid()).encode())
+            addrs = [h.rsplit(b"|", 1)[0] for h in hello]
+            server.allow([int(h.rsplit(b"|", 1)[1]) for h in hello])
             for peer in range(world):
                 if peer == rank:
                     continue
@@ -360,8 +457,21 @@ def establish(comm: int, store: Store, prefix: str, rank: int, world: int, share
                 lib.b200c_comm_mc_disable(comm)
         N.check(lib.b200c_comm_ready(comm))
         _barrier(store, prefix, "ready", rank, world, timeout_s)
+        # nobody needs the keys any more once every rank has passed "ready": rank 0 collects a "done" from
+        # every rank and deletes the whole epoch, so nothing stale is left for a later incarnation
+        store.set(f"{prefix}/done/{rank}", b"1")
+        if rank == 0:
+            for r in range(world):
+                store.get(f"{prefix}/done/{r}", timeout_s)
+            cleanup_keys(store, prefix, world)
+            store.delete(f"{base}/epoch")
+        ok_all = True
         return have_mc
     finally:
+        if not ok_all and rank == 0 and epoch is not None:
+            # a failed rendezvous must not leave a live-looking epoch behind
+            cleanup_keys(store, f"{base}/{epoch}", world)
+            store.delete(f"{base}/epoch")
         if server is not None:
             server.close()
         if own_fd >= 0:
@@ -371,6 +481,6 @@ def establish(comm: int, store: Store, prefix: str, rank: int, world: int, share
 
 
 def cleanup_keys(store: Store, prefix: str, world: int):
-    for tag in ("addr", "ipc", "imported", "mc_created", "mc_added", "mc_bound", "ready"):
+    for tag in _TAGS:
         for r in range(world):
             store.delete(f"{prefix}/{tag}/{r}")

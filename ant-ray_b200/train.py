@@ -12,6 +12,7 @@ What changes against the reference: torch.distributed is still initialised (DDP 
 group for its one-off parameter broadcast), but every per-step gradient reduction goes through
 the fused peer-memory kernel registered as DDP's comm hook — NCCL is off the hot path.
 """
+import logging
 import os
 import socket
 from dataclasses import dataclass
@@ -23,18 +24,21 @@ import torch.distributed as dist
 
 from . import ddp_hook
 
+logger = logging.getLogger(__name__)
+
 
 @dataclass
 class B200TorchConfig:
     """Drop-in for ray.train.torch.TorchConfig.  `backend` is the c10d backend used for the
     control-plane process group (nccl when GPUs are present); `grad_wire` selects what crosses
-    NVLink in the fused gradient reduction: "bf16" (bf16-compress semantics, fp32 accumulate),
-    "fp16" or "fp32" (exact torch-DDP default semantics)."""
+    NVLink in the fused gradient reduction: "fp32" (the default: exact torch-DDP default-reducer
+    semantics, so switching the import does not change training numerics), or — opt-in, like
+    registering torch's bf16_compress_hook — "bf16" / "fp16" (16-bit wire, fp32 accumulate)."""
 
     backend: Optional[str] = None
     init_method: str = "env"
     timeout_s: int = 1800
-    grad_wire: str = "bf16"
+    grad_wire: str = "fp32"
 
     @property
     def backend_cls(self):
@@ -61,7 +65,7 @@ def _free_address():
 
 
 def _setup_torch_process_group(backend: str, world_rank: int, world_size: int, init_method: str, timeout_s: int = 1800,
-                               grad_wire: str = "bf16"):
+                               grad_wire: str = "fp32"):
     """Connect torch.distributed (reference config.py:73-128) and remember the gradient wire type."""
     if backend == "nccl" and "TORCH_NCCL_ASYNC_ERROR_HANDLING" not in os.environ and "TORCH_NCCL_BLOCKING_WAIT" not in os.environ:
         os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "1"
@@ -138,6 +142,10 @@ def prepare_model(model: torch.nn.Module, move_to_device: Union[bool, torch.devi
 
         kwargs = {"device_ids": [device], "output_device": device, **parallel_strategy_kwargs}
         model = DistributedDataParallel(model, **kwargs)
-        wire = grad_wire or os.environ.get("B200COLL_GRAD_WIRE", "bf16")
+        wire = grad_wire or os.environ.get("B200COLL_GRAD_WIRE", "fp32")
+        if wire not in ("fp32", None):
+            logger.warning("B200 gradient reduction uses a %s wire (fp32 accumulate): gradients are rounded to %s on the "
+                           "way across NVLink, like torch's %s_compress_hook. Use grad_wire='fp32' for the exact "
+                           "default-reducer numerics.", wire, wire, wire)
         model.b200_grad_state = ddp_hook.register(model, wire=wire)
     return model

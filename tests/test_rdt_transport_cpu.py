@@ -76,6 +76,6 @@ def test_group_registry_and_transfer(actors):
 def test_transport_contract():
     tt = B200TensorTransport()
     assert tt.tensor_transport_backend == "B200"
-    assert B200TensorTransport.is_one_sided() is False and B200TensorTransport.can_abort_transport() is True
+    assert B200TensorTransport.is_one_sided() is False and B200TensorTransport.can_abort_transport() is False
     assert tt.extract_tensor_transport_metadata("x", []).tensor_meta == []
     tt.garbage_collect("x", TensorTransportMetadata())

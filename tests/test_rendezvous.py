@@ -101,3 +101,59 @@ def test_fd_exchange_between_two_processes(store_dir):
 def test_barrier_times_out_when_a_rank_is_missing(tmp_path):
     with pytest.raises(R.RendezvousTimeout):
         R._barrier(R.FileStore(str(tmp_path)), "p", "x", 0, 2, 0.1)
+
+
+def test_epoch_of_a_dead_incarnation_is_ignored(tmp_path):
+    """Stores outlive processes: an epoch published by a process that no longer exists (crashed job, group
+    never destroyed) must not be picked up; the live rank 0's epoch is."""
+    import subprocess
+    import sys
+
+    store = R.FileStore(str(tmp_path))
+    p = subprocess.Popen([sys.executable, "-c", "pass"])
+    p.wait()
+    store.set("g/epoch", f"stale-epoch:{p.pid}:12345".encode())
+    with pytest.raises(R.RendezvousTimeout):
+        R._agree_on_epoch(store, "g", 1, 0.3)
+    # same pid alive but another start time (pid reuse) is stale too
+    store.set("g/epoch", f"stale-epoch:{os.getpid()}:1".encode())
+    with pytest.raises(R.RendezvousTimeout):
+        R._agree_on_epoch(store, "g", 1, 0.3)
+    got = []
+    t = threading.Thread(target=lambda: got.append(R._agree_on_epoch(store, "g", 1, 10)))
+    t.start()
+    fresh = R._agree_on_epoch(store, "g", 0, 10)
+    t.join(10)
+    assert got == [fresh] and fresh != "stale-epoch"
+
+
+def test_fd_server_authenticates_requests():
+    """The abstract socket has no file permissions: requests are checked (peer uid, rank in range, pid of
+    the published group member, one fd per (rank, kind))."""
+    server = R.FdServer(world=2, rank=0)
+    r, w = os.pipe()
+    try:
+        server.offer(0, b"x", r)
+        server.allow([os.getpid(), os.getpid()])
+        with pytest.raises(OSError):
+            R.fetch_fd(server.address, 5, 0, 2)       # rank out of range
+        with pytest.raises(OSError):
+            R.fetch_fd(server.address, 0, 0, 2)       # the server's own rank
+        data, fd = R.fetch_fd(server.address, 1, 0, 5)
+        os.close(fd)
+        assert data == b"x"
+        with pytest.raises(OSError):
+            R.fetch_fd(server.address, 1, 0, 2)       # already served
+        assert server.rejected == 3
+        server2 = R.FdServer(world=2, rank=0)
+        try:
+            server2.offer(0, b"x", r)
+            server2.allow([os.getpid(), 1])           # rank 1 is some other process
+            with pytest.raises(OSError):
+                R.fetch_fd(server2.address, 1, 0, 2)
+        finally:
+            server2.close()
+    finally:
+        server.close()
+        os.close(r)
+        os.close(w)

@@ -96,7 +96,7 @@ def test_config_defaults_match_the_reference():
     cfg = T.B200TorchConfig()
     # ray.train.torch.TorchConfig: backend=None (nccl with GPUs, gloo without), init_method="env", timeout_s=1800
     assert (cfg.backend, cfg.init_method, cfg.timeout_s) == (None, "env", 1800)
-    assert cfg.grad_wire == "bf16"
+    assert cfg.grad_wire == "fp32"
     assert cfg.backend_cls is T._B200TorchBackend and T._B200TorchBackend.share_cuda_visible_devices is True
 
 
