@@ -93,6 +93,8 @@ SYMBOLS = {
     "b200c_reducescatter": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "b200c_send": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "b200c_recv": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "b200c_send_multi": (c_int, [c_void_p, c_void_p, c_size_t, POINTER(c_int), c_int, c_void_p]),
+    "b200c_recv_multi": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "b200c_barrier": (c_int, [c_void_p, c_void_p]),
     "b200c_debug_fill_flags": (c_int, [c_void_p, c_uint32]),
     "b200c_launch_count": (c_uint64, []),

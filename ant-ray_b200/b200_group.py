@@ -269,6 +269,16 @@ class PeerMemoryComm:
         s = self.stream() if stream is None else stream
         N.check(self.lib.b200c_recv(self._h(), ptr, nbytes, peer, s.cuda_stream))
 
+    def send_multi(self, ptr, nbytes, peers: List[int], stream=None):
+        """One payload to several readers (one multicast store stream when the NVSwitch object is bound)."""
+        s = self.stream() if stream is None else stream
+        arr = (ctypes.c_int * len(peers))(*peers)
+        N.check(self.lib.b200c_send_multi(self._h(), ptr, nbytes, arr, len(peers), s.cuda_stream))
+
+    def recv_multi(self, ptr, nbytes, src, stream=None):
+        s = self.stream() if stream is None else stream
+        N.check(self.lib.b200c_recv_multi(self._h(), ptr, nbytes, src, s.cuda_stream))
+
     def barrier(self):
         s = self.stream()
         N.check(self.lib.b200c_barrier(self._h(), s.cuda_stream))

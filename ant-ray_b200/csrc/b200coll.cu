@@ -130,7 +130,8 @@ struct b200c_comm {
   int sm_count = 148;
   // arena
   size_t arena_bytes = 0, gran = 0;
-  size_t off_staging = 0, off_p2p = 0, off_ll = 0, ll_words = 0, off_sym = 0, sym_bytes = 0;
+  size_t off_staging = 0, off_p2p = 0, off_mring = 0, off_ll = 0, ll_words = 0, off_sym = 0, sym_bytes = 0;
+  uint32_t mcells = 0;
   uint64_t layout_hash = 0;
   bool vmm = true;
   CUmemGenericAllocationHandle own_handle = 0;
@@ -153,6 +154,9 @@ struct b200c_comm {
   int local_scale_ctas_per_sm = 0;
   uint32_t send_cells[kMaxRanks] = {};
   uint32_t recv_cells[kMaxRanks] = {};
+  uint32_t msend_cells = 0;            // multi-reader ring of this rank: cells sent so far
+  uint32_t msend_mask = 0;             // ... and its (fixed) reader set, 0 = not chosen yet
+  uint32_t mrecv_cells[kMaxRanks] = {};
   DevComm dev{};
 };
 
@@ -303,7 +307,10 @@ extern "C" int b200c_comm_create(int rank, int world, int device, const b200c_co
   c->off_staging = kPadBytes;
   c->off_p2p = c->off_staging + 2 * cfg.staging_bytes;
   size_t p2p_bytes = world > 1 ? (size_t)kMaxRanks * cfg.p2p_slots * cfg.p2p_slot_bytes : 0;
-  c->off_ll = round_up(c->off_p2p + p2p_bytes, 4096);
+  c->mcells = world > 2 ? (cfg.p2p_slots < 64 ? cfg.p2p_slots : 64) : 0;  // with one possible reader the pairwise ring is the multi-reader ring
+  c->off_mring = round_up(c->off_p2p + p2p_bytes, 4096);
+  size_t mring_bytes = (size_t)kMaxRanks * c->mcells * cfg.p2p_slot_bytes;
+  c->off_ll = round_up(c->off_mring + mring_bytes, 4096);
   c->ll_words = world > 1 ? round_up((cfg.ll_max_bytes + 3) / 4, 4) : 0;   // whole 16-byte vectors
   size_t ll_bytes = 2 * (size_t)kMaxRanks * c->ll_words * 8;
   c->off_sym = round_up(c->off_ll + ll_bytes, 2ull << 20);
@@ -471,6 +478,8 @@ extern "C" int b200c_comm_ready(b200c_comm_t* c) {
   d.off_p2p = c->off_p2p;
   d.p2p_cell_bytes = c->cfg.p2p_slot_bytes;
   d.p2p_cells = (int)c->cfg.p2p_slots;
+  d.off_mring = c->off_mring;
+  d.mcells = (int)c->mcells;
   d.off_ll = c->off_ll;
   d.ll_words = c->ll_words;
   // a single multimem.st stream leaves the root at ~340 GB/s (measured), a unicast push at ~690 GB/s:
@@ -1015,6 +1024,7 @@ static int p2p_impl(b200c_comm* c, void* buf, size_t bytes, int peer, bool is_se
   P2PArgs a;
   memset(&a, 0, sizeof a);
   a.c = c->dev; a.buf = buf; a.bytes = bytes; a.peer = peer;
+  a.off_ring = c->off_p2p; a.off_ready = kOffP2PReady; a.off_ack = kOffP2PAck; a.cells = (int)c->cfg.p2p_slots;
   size_t cb = c->cfg.p2p_slot_bytes;
   size_t ncells = (bytes + cb - 1) / cb;
   if (ncells > 0x7fffffffull) return fail(B200C_EINVAL, "message too large for the cell ring");
@@ -1036,4 +1046,70 @@ extern "C" int b200c_send(b200c_comm_t* c, const void* buf, size_t bytes, int pe
 }
 extern "C" int b200c_recv(b200c_comm_t* c, void* buf, size_t bytes, int peer, b200c_stream_t stream) {
   return p2p_impl(c, buf, bytes, peer, false, (cudaStream_t)stream);
+}
+
+extern "C" int b200c_send_multi(b200c_comm_t* c, const void* buf, size_t bytes, const int* peers, int npeers, b200c_stream_t stream) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (!peers || npeers < 1) return fail(B200C_EINVAL, "no readers");
+  uint32_t mask = 0;
+  for (int i = 0; i < npeers; i++) {
+    if (peers[i] < 0 || peers[i] >= c->world) return fail(B200C_EINVAL, "bad peer %d", peers[i]);
+    if (peers[i] == c->rank) return fail(B200C_EINVAL, "send to self (rank %d)", peers[i]);
+    if (mask & (1u << peers[i])) return fail(B200C_EINVAL, "peer %d listed twice", peers[i]);
+    mask |= 1u << peers[i];
+  }
+  if (npeers == 1 || c->mcells == 0) {   // a single reader is the pairwise ring (the reader calls b200c_recv)
+    if (npeers != 1) return fail(B200C_ESTATE, "multi-reader ring unavailable");
+    return p2p_impl(c, const_cast<void*>(buf), bytes, peers[0], true, (cudaStream_t)stream);
+  }
+  if (c->msend_mask && c->msend_mask != mask)
+    return fail(B200C_EUNSUPPORTED, "rank %d already multi-sends to reader set 0x%x; a second reader set (0x%x) must use per-reader sends "
+                "(ring positions are counted per source, so every reader has to see every message)", c->rank, c->msend_mask, mask);
+  if (bytes == 0) return B200C_OK;
+  if (!buf) return fail(B200C_EINVAL, "null buffer");
+  DeviceGuard g(c->device);
+  P2PArgs a;
+  memset(&a, 0, sizeof a);
+  a.c = c->dev; a.buf = const_cast<void*>(buf); a.bytes = bytes; a.peer = -1; a.reader_mask = mask;
+  a.off_ring = c->off_mring; a.off_ready = kOffMReady; a.off_ack = kOffMAck; a.cells = (int)c->mcells;
+  size_t cb = c->cfg.p2p_slot_bytes;
+  size_t ncells = (bytes + cb - 1) / cb;
+  if (ncells > 0x7fffffffull) return fail(B200C_EINVAL, "message too large for the cell ring");
+  a.first_cell = c->msend_cells; a.ncells = (uint32_t)ncells;
+  uint32_t grid = (uint32_t)ncells;
+  uint32_t lim = c->cfg.max_blocks < c->mcells ? c->cfg.max_blocks : c->mcells;
+  if (grid > lim) grid = lim;
+  k_send_multi<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+  rc = launch_check(c, "send_multi");
+  if (rc) return rc;
+  c->msend_cells += (uint32_t)ncells;
+  c->msend_mask = mask;
+  return B200C_OK;
+}
+
+extern "C" int b200c_recv_multi(b200c_comm_t* c, void* buf, size_t bytes, int src, b200c_stream_t stream) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (src < 0 || src >= c->world || src == c->rank) return fail(B200C_EINVAL, "bad source %d", src);
+  if (c->mcells == 0) return p2p_impl(c, buf, bytes, src, false, (cudaStream_t)stream);
+  if (bytes == 0) return B200C_OK;
+  if (!buf) return fail(B200C_EINVAL, "null buffer");
+  DeviceGuard g(c->device);
+  P2PArgs a;
+  memset(&a, 0, sizeof a);
+  a.c = c->dev; a.buf = buf; a.bytes = bytes; a.peer = src;
+  a.off_ring = c->off_mring; a.off_ready = kOffMReady; a.off_ack = kOffMAck; a.cells = (int)c->mcells;
+  size_t cb = c->cfg.p2p_slot_bytes;
+  size_t ncells = (bytes + cb - 1) / cb;
+  if (ncells > 0x7fffffffull) return fail(B200C_EINVAL, "message too large for the cell ring");
+  a.first_cell = c->mrecv_cells[src]; a.ncells = (uint32_t)ncells;
+  uint32_t grid = (uint32_t)ncells;
+  uint32_t lim = c->cfg.max_blocks < c->mcells ? c->cfg.max_blocks : c->mcells;
+  if (grid > lim) grid = lim;
+  k_recv<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+  rc = launch_check(c, "recv_multi");
+  if (rc) return rc;
+  c->mrecv_cells[src] += (uint32_t)ncells;
+  return B200C_OK;
 }

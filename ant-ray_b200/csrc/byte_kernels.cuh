@@ -173,14 +173,21 @@ __global__ void __launch_bounds__(32) k_barrier(const __grid_constant__ CollArgs
 // ---------------------------------------------------------------------------------------------
 // p2p: ring of cells in the receiver's arena, one ready flag and one ack flag per cell.
 // Cell k of the pair's lifetime lives at ring position k % cells and carries flag value k+1.
+// The same two kernels serve the pairwise rings (one per ordered pair) and the multi-reader rings
+// (one per source rank, identical offset in every arena): only the offsets in P2PArgs differ.
 // ---------------------------------------------------------------------------------------------
 struct P2PArgs {
   DevComm c;
   void* buf;          // user buffer (send: source, recv: destination)
   size_t bytes;
-  int peer;
+  int peer;           // recv: source rank; pairwise send: destination rank
   uint32_t first_cell;  // cumulative cell index of this message's first cell
   uint32_t ncells;
+  size_t off_ring;    // arena offset of ring [8 src][cells][cell_bytes]
+  size_t off_ready;   // pad offset of ready[8 src][kMaxCells]   (lives on the receiver)
+  size_t off_ack;     // pad offset of ack[8 dst][kMaxCells]     (lives on the sender)
+  int cells;
+  uint32_t reader_mask;  // multi-reader send: bit j = rank j receives this message
 };
 
 __global__ void __launch_bounds__(kThreads) k_send(const __grid_constant__ P2PArgs a) {
@@ -190,19 +197,56 @@ __global__ void __launch_bounds__(kThreads) k_send(const __grid_constant__ P2PAr
   const uint8_t* src = static_cast<const uint8_t*>(a.buf);
   for (uint32_t i = blockIdx.x; i < a.ncells; i += gridDim.x) {
     uint32_t k = a.first_cell + i;
-    uint32_t pos = k % (uint32_t)c.p2p_cells;
+    uint32_t pos = k % (uint32_t)a.cells;
     // the previous occupant of this ring position (cell k - cells) must have been consumed
-    if (k >= (uint32_t)c.p2p_cells) {
-      const uint32_t* ack = reinterpret_cast<const uint32_t*>(c.arena[r] + kOffP2PAck) + (size_t)d * kMaxCells + pos;
-      if (!block_wait_one(ack, k + 1 - (uint32_t)c.p2p_cells, c, d, 4)) return;
+    if (k >= (uint32_t)a.cells) {
+      const uint32_t* ack = reinterpret_cast<const uint32_t*>(c.arena[r] + a.off_ack) + (size_t)d * kMaxCells + pos;
+      if (!block_wait_one(ack, k + 1 - (uint32_t)a.cells, c, d, 4)) return;
     }
     size_t off = (size_t)i * cb;
     size_t cnt = a.bytes - off < cb ? a.bytes - off : cb;
-    uint8_t* dst = reinterpret_cast<uint8_t*>(c.arena[d] + c.off_p2p + ((size_t)r * c.p2p_cells + pos) * cb);
+    uint8_t* dst = reinterpret_cast<uint8_t*>(c.arena[d] + a.off_ring + ((size_t)r * a.cells + pos) * cb);
     copy_tile<uint8_t, false>(dst, src + off, cnt);
     __syncthreads();
     if (threadIdx.x == 0)
-      st_release_sys(reinterpret_cast<uint32_t*>(c.arena[d] + kOffP2PReady) + (size_t)r * kMaxCells + pos, k + 1);
+      st_release_sys(reinterpret_cast<uint32_t*>(c.arena[d] + a.off_ready) + (size_t)r * kMaxCells + pos, k + 1);
+  }
+}
+
+// Multi-reader send (the reference sends once per reader: torch_tensor_accelerator_channel.py:586-590,
+// "TODO: If there are multiple readers, can replace with a broadcast").  Every cell is written ONCE to
+// the multicast address of this rank's ring — the NVSwitch replicates it into every arena — when a
+// multicast object is bound and the source is 16-byte aligned; otherwise once per reader by unicast.
+// Flow control is per reader: a ring position is reused only after every reader of the (fixed) reader
+// set has acknowledged its previous occupant.
+__global__ void __launch_bounds__(kThreads) k_send_multi(const __grid_constant__ P2PArgs a) {
+  const DevComm& c = a.c;
+  const int r = c.rank, W = c.world, t = threadIdx.x;
+  const size_t cb = c.p2p_cell_bytes;
+  const uint8_t* src = static_cast<const uint8_t*>(a.buf);
+  const bool reader = t < W && ((a.reader_mask >> t) & 1u);
+  for (uint32_t i = blockIdx.x; i < a.ncells; i += gridDim.x) {
+    uint32_t k = a.first_cell + i;
+    uint32_t pos = k % (uint32_t)a.cells;
+    if (k >= (uint32_t)a.cells) {
+      int ok = 1;
+      if (reader) ok = wait_flag(reinterpret_cast<const uint32_t*>(c.arena[r] + a.off_ack) + (size_t)t * kMaxCells + pos, k + 1 - (uint32_t)a.cells, c, t, 4);
+      if (!__syncthreads_and(ok)) return;
+    }
+    size_t off = (size_t)i * cb;
+    size_t cnt = a.bytes - off < cb ? a.bytes - off : cb;
+    const size_t cell_off = a.off_ring + ((size_t)r * a.cells + pos) * cb;
+    size_t done = 0;
+    if (c.mc_arena && aligned16(src + off)) {
+      multicast_tile<false>(c.mc_arena + cell_off, reinterpret_cast<const uint4*>(src + off), cnt / 16);
+      done = cnt / 16 * 16;
+    }
+    if (done < cnt) {
+      for (int j = 0; j < W; j++)
+        if ((a.reader_mask >> j) & 1u) copy_tile<uint8_t, false>(reinterpret_cast<uint8_t*>(c.arena[j] + cell_off) + done, src + off + done, cnt - done);
+    }
+    __syncthreads();
+    if (reader) st_release_sys(reinterpret_cast<uint32_t*>(c.arena[t] + a.off_ready) + (size_t)r * kMaxCells + pos, k + 1);
   }
 }
 
@@ -213,16 +257,16 @@ __global__ void __launch_bounds__(kThreads) k_recv(const __grid_constant__ P2PAr
   uint8_t* dstbuf = static_cast<uint8_t*>(a.buf);
   for (uint32_t i = blockIdx.x; i < a.ncells; i += gridDim.x) {
     uint32_t k = a.first_cell + i;
-    uint32_t pos = k % (uint32_t)c.p2p_cells;
-    const uint32_t* ready = reinterpret_cast<const uint32_t*>(c.arena[r] + kOffP2PReady) + (size_t)s * kMaxCells + pos;
+    uint32_t pos = k % (uint32_t)a.cells;
+    const uint32_t* ready = reinterpret_cast<const uint32_t*>(c.arena[r] + a.off_ready) + (size_t)s * kMaxCells + pos;
     if (!block_wait_one(ready, k + 1, c, s, 3)) return;
     size_t off = (size_t)i * cb;
     size_t cnt = a.bytes - off < cb ? a.bytes - off : cb;
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(c.arena[r] + c.off_p2p + ((size_t)s * c.p2p_cells + pos) * cb);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(c.arena[r] + a.off_ring + ((size_t)s * a.cells + pos) * cb);
     copy_tile<uint8_t, true>(dstbuf + off, src, cnt);
     __syncthreads();
     if (threadIdx.x == 0)
-      st_release_sys(reinterpret_cast<uint32_t*>(c.arena[s] + kOffP2PAck) + (size_t)r * kMaxCells + pos, k + 1);
+      st_release_sys(reinterpret_cast<uint32_t*>(c.arena[s] + a.off_ack) + (size_t)r * kMaxCells + pos, k + 1);
   }
 }
 

@@ -35,7 +35,9 @@ constexpr size_t kOffPipeB = kOffPipeA + kMaxBlocks * 8 * 4;  // u32 [kMaxBlocks
 constexpr size_t kOffP2PReady = kOffPipeB + kMaxBlocks * 8 * 4;  // u32 [8 src][kMaxCells]
 constexpr int kMaxCells = 1024;
 constexpr size_t kOffP2PAck = kOffP2PReady + 8 * kMaxCells * 4;  // u32 [8 dst][kMaxCells]
-constexpr size_t kPadUsed = kOffP2PAck + 8 * kMaxCells * 4;
+constexpr size_t kOffMReady = kOffP2PAck + 8 * kMaxCells * 4;  // u32 [8 src][kMaxCells]  multi-reader ring: cell ready (on each reader)
+constexpr size_t kOffMAck = kOffMReady + 8 * kMaxCells * 4;    // u32 [8 dst][kMaxCells]  multi-reader ring: cell consumed (on the source)
+constexpr size_t kPadUsed = kOffMAck + 8 * kMaxCells * 4;
 static_assert(kPadUsed <= kPadBytes, "signal pad overflow");
 
 // host-pinned, device-mapped status block
@@ -59,6 +61,8 @@ struct DevComm {
   size_t off_p2p;           // arena offset of the p2p rings [8 src][cells][cell_bytes]
   size_t p2p_cell_bytes;
   int p2p_cells;
+  size_t off_mring;         // arena offset of the multi-reader rings [8 src][mcells][cell_bytes]
+  int mcells;
   size_t off_ll;            // arena offset of the LL (packed data+flag) region: [2 halves][8 src][ll_words] u64
   size_t ll_words;          // 32-bit payload words per source slot (one u64 {data, flag} each)
 };

@@ -217,6 +217,17 @@ int b200c_reducescatter(b200c_comm_t* comm, const void* const* send_ptrs, void* 
 int b200c_send(b200c_comm_t* comm, const void* buf, size_t bytes, int peer, b200c_stream_t stream);
 int b200c_recv(b200c_comm_t* comm, void* buf, size_t bytes, int peer, b200c_stream_t stream);
 
+/* Multi-reader send: torch_tensor_accelerator_channel.py:586-590 sends the same tensor once per reader
+ * ("TODO: If there are multiple readers, can replace with a broadcast").  One call delivers `bytes` to
+ * every rank in `peers`; with a bound multicast object the payload leaves this GPU once (multimem.st)
+ * and the NVSwitch replicates it.  Every reader receives with b200c_recv_multi(src = the sender).
+ * A source rank multi-sends to ONE reader set for the lifetime of the communicator (ring positions are
+ * counted per source); another reader set -> B200C_EUNSUPPORTED, use per-reader b200c_send.  With a
+ * single reader, or a world of two, both calls are the pairwise b200c_send / b200c_recv. */
+int b200c_send_multi(b200c_comm_t* comm, const void* buf, size_t bytes, const int* peers, int npeers,
+                     b200c_stream_t stream);
+int b200c_recv_multi(b200c_comm_t* comm, void* buf, size_t bytes, int src, b200c_stream_t stream);
+
 /* barrier: nccl_collective_group.py:192-210 (an allreduce of [1] in the reference). */
 int b200c_barrier(b200c_comm_t* comm, b200c_stream_t stream);
 

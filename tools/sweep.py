@@ -62,6 +62,9 @@ def main():
     ap.add_argument("--no-nccl", action="store_true")
     ap.add_argument("--per-iter", action="store_true", help="time every call separately; report min/median/max")
     ap.add_argument("--blocks-list", default="", help="extra communicators with these max_blocks, e.g. 592,1184")
+    ap.add_argument("--variants", default="", help="extra communicators with config overrides, timed on one algorithm each: "
+                    "'label:algo:key=val,key=val;label2:algo2:...' e.g. 'sym64:nvls_sym:nvls_blocks=64;r16:nvls_pipe:granule_bytes=16384'")
+    ap.add_argument("--iters-scale", type=float, default=1.0)
     a = ap.parse_args()
     global PER_ITER
     PER_ITER = a.per_iter
@@ -79,7 +82,17 @@ def main():
     extra = {}
     for mb in [int(x) for x in a.blocks_list.split(",") if x]:
         extra[mb] = PeerMemoryComm(world, rank, f"sweep-mb{mb}", local, None, make_config(**{**kw, "max_blocks": mb}))
-    algos = {"auto": N.ALGO_AUTO, "oneshot": N.ALGO_ONESHOT, "twoshot": N.ALGO_TWOSHOT, "nvls": N.ALGO_NVLS, "nvls_sym": N.ALGO_NVLS,
+    variants = []
+    for spec in [v for v in a.variants.split(";") if v]:
+        label, algo_name, *rest = spec.split(":")
+        over = dict(kw)
+        for item in (rest[0].split(",") if rest and rest[0] else []):
+            k_, v_ = item.split("=")
+            over[k_] = int(v_)
+        if algo_name == "nvls_sym":
+            over["symmetric_bytes"] = max(sizes)
+        variants.append((label, algo_name, PeerMemoryComm(world, rank, f"sweep-var-{label}", local, None, make_config(**over))))
+    algos = {"auto": N.ALGO_AUTO, "ll": N.ALGO_LL, "oneshot": N.ALGO_ONESHOT, "twoshot": N.ALGO_TWOSHOT, "nvls": N.ALGO_NVLS, "nvls_sym": N.ALGO_NVLS,
              "nvls_pipe": N.ALGO_NVLS_PIPE}
     out = {"world": world, "dtype": a.dtype, "multicast": bool(comm.multicast), "nccl_version": ".".join(map(str, torch.cuda.nccl.version())),
            "max_blocks": comm.config.max_blocks, "rows": []}
@@ -88,12 +101,26 @@ def main():
         for size in sizes:
             n = size // esz
             nbuf = max(1, min(16, (256 << 20) // size))
-            iters = 200 if size <= (1 << 20) else (40 if size <= (64 << 20) else 10)
+            iters = max(3, int((200 if size <= (1 << 20) else (40 if size <= (64 << 20) else 10)) * a.iters_scale))
             row = {"op": op, "bytes": size}
             if op == "allreduce":
                 bufs = [torch.ones(n, dtype=dtype, device="cuda") for _ in range(nbuf)]
-                for name in a.algos.split(","):
+                for label, algo_name, cx in variants:
+                    if algo_name.startswith("nvls") and not cx.multicast:
+                        continue
+                    if algo_name == "ll" and size > cx.config.ll_max_bytes:
+                        continue
+                    if algo_name == "nvls_sym":
+                        vb = [cx.symmetric_tensor((n,), dtype)]
+                        us = timeit(lambda b: cx.allreduce(b.data_ptr(), b.data_ptr(), n, nat, N.SUM, N.ALGO_NVLS), vb, iters, world)
+                    else:
+                        us = timeit(lambda b: cx.allreduce(b.data_ptr(), b.data_ptr(), n, nat, N.SUM, algos[algo_name]), bufs, iters, world)
+                    row[label + "_us"] = round(us, 2)
+                    row[label + "_busbw"] = round(size / us / 1e3 * k, 1)
+                for name in [x for x in a.algos.split(",") if x]:
                     if name in ("nvls", "nvls_sym", "nvls_pipe") and not comm.multicast:
+                        continue
+                    if name == "ll" and size > comm.config.ll_max_bytes:
                         continue
                     if name == "oneshot" and size * world > (a.staging_mb << 20) * 4:
                         continue
@@ -168,7 +195,7 @@ def main():
             if rank == 0:
                 print("#", json.dumps(row), flush=True)
     comm.check()
-    for cx in extra.values():
+    for cx in list(extra.values()) + [v[2] for v in variants]:
         cx.check(); cx.destroy()
     if rank == 0:
         print(json.dumps(out))
