@@ -168,8 +168,8 @@ class PeerMemoryComm:
         N.check(self.lib.b200c_comm_create(rank, world_size, self.device, ctypes.byref(self.config), ctypes.byref(handle)))
         self.handle = handle
         try:
-            self.multicast = rendezvous.establish(handle, self.store, key, rank, world_size, self.config.share_mode,
-                                                  want_mc, timeout_s)
+            self.multicast, self.epoch = rendezvous.establish(handle, self.store, key, rank, world_size, self.config.share_mode,
+                                                              want_mc, timeout_s)
         except BaseException:
             self.lib.b200c_comm_destroy(handle)
             self.handle = None

@@ -56,10 +56,23 @@ class PipeMetaChannel:
 
 
 class TensorListChannel:
-    """Lists of GPU tensors: metadata over `meta_channel`, payload over the communicator."""
+    """Lists of GPU tensors: metadata, then payload over the communicator.
+
+    Two things the reference leaves as TODOs are used when the communicator offers them
+    (B200Communicator does; the CPU test double and foreign communicators do not):
+      * `inline_metadata`: shape and dtype ride in a binary header next to the communicator's cell ring
+        (`send_with_header` / `recv_with_header`), so dynamic shapes need no second channel and no
+        pickle (reference :574-578, :592-608); `meta_channel` is then only used if inlining is refused
+        (`inline_metadata=False`);
+      * `multi_reader`: with several readers every tensor is sent ONCE (`send_multi`, a multicast store
+        stream) instead of once per reader (reference :586-590, "TODO: ... can replace with a
+        broadcast").  A writer can multicast to one reader set only; further channels of the same
+        writer with other readers must be created with `multicast=False`.
+    Both choices are made identically on the writer and on every reader from the constructor
+    arguments, which the creator of the channel passes to all endpoints alike."""
 
     def __init__(self, communicator, writer_rank: int, reader_ranks: List[int], meta_channel, static_shape: bool = False,
-                 allocator=default_allocator, require_cuda: bool = True):
+                 allocator=default_allocator, require_cuda: bool = True, inline_metadata: bool = True, multicast: bool = True):
         self._comm = communicator
         self._writer_rank, self._reader_ranks = writer_rank, list(reader_ranks)
         self._meta = meta_channel
@@ -70,6 +83,8 @@ class TensorListChannel:
         me = communicator.get_self_rank()
         self._is_writer = me == writer_rank
         self._is_reader = me in self._reader_ranks
+        self._inline = bool(inline_metadata and getattr(communicator, "inline_metadata", False))
+        self._multi = bool(multicast and len(self._reader_ranks) > 1 and getattr(communicator, "multi_reader", False))
 
     def _send_metadata(self, tensors):
         import torch
@@ -92,20 +107,46 @@ class TensorListChannel:
     def write(self, tensors: List["torch.Tensor"], timeout: Optional[float] = None):
         assert self._is_writer, "this actor is not the writer of the channel"
         meta = self._send_metadata(tensors)
-        if meta is not None:
+        with_header = meta is not None and self._inline
+        if meta is not None and not self._inline:
             self._meta.write(meta)  # before the sends, so the reader can launch the matching recv
-        for t in tensors:
+        if with_header and not tensors:
+            self._comm.announce_empty(self._reader_ranks)
+        for i, t in enumerate(tensors):
+            if self._multi:
+                if with_header:
+                    self._comm.send_with_header(t, self._reader_ranks, i, len(tensors))
+                else:
+                    self._comm.send_multi(t, self._reader_ranks)
+                continue
             for rank in self._reader_ranks:
-                self._comm.send(t, rank)
+                if with_header:
+                    self._comm.send_with_header(t, rank, i, len(tensors))
+                else:
+                    self._comm.send(t, rank)
 
     def read(self, timeout: Optional[float] = None) -> List["torch.Tensor"]:
         assert self._is_reader, "this actor is not a reader of the channel"
         meta = self._static_meta
+        if meta is None and self._inline:
+            out, metas = [], []
+            t, _, count = self._comm.recv_with_header(self._writer_rank, self._allocator, timeout, multi=self._multi)
+            for i in range(count):
+                if i:
+                    t, index, cnt = self._comm.recv_with_header(self._writer_rank, self._allocator, timeout, multi=self._multi)
+                    if index != i or cnt != count:
+                        raise ValueError(f"tensor header out of sequence: got {index}/{cnt}, expected {i}/{count}")
+                out.append(t)
+                metas.append(TorchTensorMetadata(tuple(t.shape), t.dtype))
+            if self._static_shape:
+                self._static_meta = metas
+            return out
         if meta is None:
             meta = self._meta.read(timeout)
             if self._static_shape:
                 self._static_meta = meta
-        return [self._comm.recv(m.shape, m.dtype, self._writer_rank, self._allocator) for m in meta]
+        recv = self._comm.recv_multi if self._multi else self._comm.recv
+        return [recv(m.shape, m.dtype, self._writer_rank, self._allocator) for m in meta]
 
     def close(self):
         self._meta.close()

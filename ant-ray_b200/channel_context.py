@@ -42,22 +42,36 @@ class ChannelContext:
             return cls._current
 
 
-def _do_get_unique_communication_id(self, communicator_cls):
+def _do_get_unique_communication_id(self, communicator_cls=None):
+    if communicator_cls is None:  # the registered (or default) accelerator context decides, as in the reference
+        from .accelerator_context import AcceleratorContext
+
+        return AcceleratorContext.get().generate_communicator_id()
     return communicator_cls.generate_communicator_id()
 
 
 def _do_init_communicator(self, group_id, world_size, comm_id, rank, actor_handles, use_communication_streams,
                           custom_communicator=None, communicator_cls=None):
+    """Runs on every actor (reference torch_tensor_accelerator_channel.py:652-680).  The default path builds
+    the class the accelerator-context registry names — B200Communicator once `register_b200()` has run, or by
+    default on a CUDA device outside Ray — exactly the way the reference calls it: positional
+    (world_size, comm_id, rank, actor_handles, current stream, use_communication_streams).
+    `communicator_cls` overrides the registry for one group (tests)."""
+    from .accelerator_context import AcceleratorContext
+
     ctx = ChannelContext.get_current()
     if custom_communicator is not None:
         custom_communicator.initialize(rank)
         ctx.communicators[group_id] = custom_communicator
         return rank
-    import torch
-
-    assert torch.cuda.is_available(), "Actors participating in a communication group must have a GPU assigned"
-    ctx.communicators[group_id] = communicator_cls(world_size, comm_id, rank, actor_handles, torch.cuda.current_stream(),
-                                                   use_communication_streams)
+    actx = AcceleratorContext.get()
+    assert actx.accelerator_count > 0, "Actors participating in Communication group must have at least one Accelerator assigned"
+    if communicator_cls is not None:
+        ctx.communicators[group_id] = communicator_cls(world_size, comm_id, rank, actor_handles, actx.current_stream(),
+                                                       use_communication_streams)
+    else:
+        ctx.communicators[group_id] = actx.create_communicator(world_size, comm_id, rank, actor_handles, actx.current_stream(),
+                                                               use_communication_streams)
     return rank
 
 
@@ -72,8 +86,6 @@ def _do_destroy_communicator(self, group_id):
 def init_communicator(actors: list, custom_communicator=None, use_communication_streams: bool = False,
                       communicator_cls=None) -> str:
     """Create (or adopt) a communicator on every actor; returns the group id."""
-    if communicator_cls is None:
-        from .communicator import B200Communicator as communicator_cls  # noqa: N813
     keys = {_xc._actor_key(a) for a in actors}
     assert len(keys) == len(actors), "Actors must be unique"
     comm_id = _xc._resolve(actors[0].__ray_call__.remote(_do_get_unique_communication_id,

@@ -373,7 +373,8 @@ def establish(comm: int, store: Store, prefix: str, rank: int, world: int, share
               want_multicast: bool, timeout_s: float = 60.0) -> bool:
     """Drive a freshly created native communicator (`b200c_comm_create`) to the ready state.
 
-    Returns True when the NVSwitch multicast object is bound on every rank.
+    Returns (multicast, epoch): whether the NVSwitch multicast object is bound on every rank, and the
+    random id of this incarnation of the group (the same string on every rank).
     """
     lib = N.load()
     exp = N.Export()
@@ -382,7 +383,7 @@ def establish(comm: int, store: Store, prefix: str, rank: int, world: int, share
         if exp.fd >= 0:
             os.close(exp.fd)
         N.check(lib.b200c_comm_ready(comm))
-        return False
+        return False, uuid.uuid4().hex
     server: Optional[FdServer] = None
     own_fd = exp.fd
     mc_fd_own = -1
@@ -466,7 +467,7 @@ def establish(comm: int, store: Store, prefix: str, rank: int, world: int, share
             cleanup_keys(store, prefix, world)
             store.delete(f"{base}/epoch")
         ok_all = True
-        return have_mc
+        return have_mc, epoch
     finally:
         if not ok_all and rank == 0 and epoch is not None:
             # a failed rendezvous must not leave a live-looking epoch behind
