@@ -968,24 +968,29 @@ extern "C" int b200c_broadcast(b200c_comm_t* c, void* buf, size_t count, int dty
     a.n = n; a.root = root;
     int grid;
     uint32_t rounds = 0;
-    // every rank takes the same decision from (n, world, multicast): the buffer address is NOT part of it
-    // except through the alignment every rank checks alike for its own pointer — an unaligned root falls
-    // back inside the kernel only in the unicast/multicast modes, so rounds mode requires torch-style
-    // (>= 16-byte aligned) buffers on every rank and is skipped otherwise by the size test below.
+    // every rank takes the same decision from (n, world, multicast)
     const bool mc = c->mc_arena && c->bcast_mc;
-    const bool rounds_mode = mc && W > 2 && c->cfg.bcast_rounds_min_bytes && n >= c->cfg.bcast_rounds_min_bytes && n % 16 == 0;
-    if (rounds_mode && (((uintptr_t)a.in) & 15) != 0)
+    const bool big = c->cfg.bcast_rounds_min_bytes && n >= c->cfg.bcast_rounds_min_bytes;
+    const bool mc_rounds = big && mc && W > 2 && n % 16 == 0;     // scatter + multicast allgather
+    const bool uc_rounds = big && !mc_rounds && (W == 2 || !mc);  // pipelined unicast push
+    if (mc_rounds && (((uintptr_t)a.in) & 15) != 0)
       return fail(B200C_EINVAL, "broadcast of >= %llu bytes needs a 16-byte aligned buffer", (unsigned long long)c->cfg.bcast_rounds_min_bytes);
-    if (rounds_mode) {
+    if (mc_rounds) {
       a.chunk = round_up((n + W - 1) / W, 16);
       plan_rounds(a.chunk, 1, 16, c->cfg.max_blocks, c->cfg.granule_bytes, &a.tile, &grid, &rounds);
       a.pipe_base = c->pipe_base;
       a.symmetric = 2;
+    } else if (uc_rounds) {
+      a.chunk = round_up(n, 16);
+      plan_rounds(a.chunk, 1, 16, c->cfg.max_blocks, c->cfg.granule_bytes, &a.tile, &grid, &rounds);
+      a.pipe_base = c->pipe_base;
+      a.symmetric = 3;
     } else {
       a.chunk = round_up(n, 16);
       a.symmetric = (mc && n >= 65536) ? 1 : 0;  // multicast store from the root (same choice on every rank)
       plan_tiles(n, 1, 16, c->cfg.max_blocks, kMinTileBytes, c->cfg.granule_bytes, &a.tile, &grid);
     }
+    const bool rounds_mode = mc_rounds || uc_rounds;
     a.sig = make_sig(OPC_BROADCAST, dtype, 0, n, root, a.symmetric);
     if (rounds_mode) k_broadcast_rounds<<<grid, kThreads, 0, s>>>(a);
     else k_broadcast<<<grid, kThreads, 0, s>>>(a);
@@ -1033,6 +1038,23 @@ static int p2p_impl(b200c_comm* c, void* buf, size_t bytes, int peer, bool is_se
   // no block may wait on a cell that one of its own later iterations has to free: grid <= ring size
   uint32_t grid = (uint32_t)ncells;
   uint32_t lim = c->cfg.max_blocks < c->cfg.p2p_slots ? c->cfg.max_blocks : c->cfg.p2p_slots;
+  if (is_send) {
+    // A sender block publishes `batch` cells per release fence (stride grid).  Small messages keep batch 1
+    // (one cell per block: lowest latency); large ones amortise the fence.  All cells of one pass over the
+    // grid must fit in the ring together, or a block would wait for an ack that only a later cell of its own
+    // pass triggers: grid * batch <= ring cells.
+    static int env_batch = [] { const char* e = getenv("B200COLL_SEND_BATCH"); return e ? atoi(e) : 0; }();
+    uint32_t batch = (uint32_t)((ncells + lim - 1) / lim);
+    if (env_batch > 0) batch = (uint32_t)env_batch;
+    if (batch < 1) batch = 1;
+    if (batch > (uint32_t)kSendBatch) batch = kSendBatch;
+    a.batch = (int)batch;
+    uint32_t lim_s = c->cfg.p2p_slots / batch;
+    if (lim_s < 1) lim_s = 1;
+    if (lim > lim_s) lim = lim_s;
+    uint32_t want = ((uint32_t)ncells + batch - 1) / batch;
+    grid = want < 1 ? 1 : want;
+  }
   if (grid > lim) grid = lim;
   if (is_send) k_send<<<grid, kThreads, 0, s>>>(a);
   else k_recv<<<grid, kThreads, 0, s>>>(a);

@@ -106,13 +106,38 @@ __global__ void __launch_bounds__(kThreads) k_broadcast_rounds(const __grid_cons
   check_signature(a);
   const size_t half_off = c.off_staging + (size_t)(a.seq & 1) * c.staging_bytes;
   uint8_t* mine = reinterpret_cast<uint8_t*>(c.arena[r] + half_off);
-  char* mc = c.mc_arena + half_off;
   const size_t first = (size_t)blockIdx.x * a.tile, step = (size_t)gridDim.x * a.tile;
   if (first >= a.chunk) return;
   const int R = (int)((a.chunk - first + step - 1) / step);
   const int t = threadIdx.x;
   auto lo_of = [&](int q) { return first + (size_t)q * step; };
   auto hi_of = [&](int q) { size_t h = first + (size_t)q * step + a.tile; return h < a.chunk ? h : a.chunk; };
+  if (a.symmetric == 3) {
+    // Unicast rounds (world of two, or no multicast object): chunk == the whole message.  The root pushes
+    // granule q to every peer and raises pipeA; a peer copies granule q out as soon as it has landed, so
+    // the root's NVLink stores and the peers' local copies overlap instead of running back to back.
+    if (r == root) {
+      const uint8_t* src = static_cast<const uint8_t*>(a.in);
+      for (int q = 0; q < R; q++) {
+        const size_t g0 = lo_of(q), cnt = clip_count(g0, hi_of(q), a.n);
+        for (int k = 1; k < W && cnt; k++) {
+          int j = r + k; if (j >= W) j -= W;
+          copy_tile<uint8_t, false>(reinterpret_cast<uint8_t*>(c.arena[j] + half_off) + g0, src + g0, cnt);
+        }
+        round_signal(kOffPipeA, a.pipe_base + q + 1, c);
+      }
+      return;
+    }
+    uint8_t* out = static_cast<uint8_t*>(a.out);
+    const uint32_t* fA = reinterpret_cast<const uint32_t*>(c.arena[r] + kOffPipeA) + (size_t)blockIdx.x * 8 + root;
+    for (int q = 0; q < R; q++) {
+      if (!block_wait_one(fA, a.pipe_base + q + 1, c, root, 1)) return;
+      const size_t g0 = lo_of(q), cnt = clip_count(g0, hi_of(q), a.n);
+      if (cnt) copy_tile<uint8_t, true>(out + g0, mine + g0, cnt);
+    }
+    return;
+  }
+  char* mc = c.mc_arena + half_off;
   if (r == root) {
     const uint8_t* src = static_cast<const uint8_t*>(a.in);
     for (int q = 0; q < R; q++) {
@@ -188,28 +213,50 @@ struct P2PArgs {
   size_t off_ack;     // pad offset of ack[8 dst][kMaxCells]     (lives on the sender)
   int cells;
   uint32_t reader_mask;  // multi-reader send: bit j = rank j receives this message
+  int batch;          // pairwise send: cells published per release fence (1..kSendBatch)
 };
+
+// A system-scope release fence costs ~3 us on a quiet SM and ~15 us while the SM's other warps stream
+// stores to the peer (profiles/r02_probe_2gpu_exp.log, E3), so a sender block publishes kSendBatch
+// cells per fence: copy cells i, i+grid, ... , then one __syncthreads + fence and one flag per cell.
+constexpr int kSendBatch = 4;
 
 __global__ void __launch_bounds__(kThreads) k_send(const __grid_constant__ P2PArgs a) {
   const DevComm& c = a.c;
-  const int r = c.rank, d = a.peer;
+  const int r = c.rank, d = a.peer, t = threadIdx.x;
   const size_t cb = c.p2p_cell_bytes;
   const uint8_t* src = static_cast<const uint8_t*>(a.buf);
-  for (uint32_t i = blockIdx.x; i < a.ncells; i += gridDim.x) {
-    uint32_t k = a.first_cell + i;
-    uint32_t pos = k % (uint32_t)a.cells;
-    // the previous occupant of this ring position (cell k - cells) must have been consumed
-    if (k >= (uint32_t)a.cells) {
-      const uint32_t* ack = reinterpret_cast<const uint32_t*>(c.arena[r] + a.off_ack) + (size_t)d * kMaxCells + pos;
-      if (!block_wait_one(ack, k + 1 - (uint32_t)a.cells, c, d, 4)) return;
+  const int B = a.batch;
+  for (uint32_t i0 = blockIdx.x; i0 < a.ncells; i0 += gridDim.x * B) {
+    // the previous occupants of these ring positions (cell k - cells) must have been consumed
+    int ok = 1;
+    if (t < B) {
+      uint32_t i = i0 + (uint32_t)t * gridDim.x, k = a.first_cell + i;
+      if (i < a.ncells && k >= (uint32_t)a.cells) {
+        uint32_t pos = k % (uint32_t)a.cells;
+        ok = wait_flag(reinterpret_cast<const uint32_t*>(c.arena[r] + a.off_ack) + (size_t)d * kMaxCells + pos, k + 1 - (uint32_t)a.cells, c, d, 4);
+      }
     }
-    size_t off = (size_t)i * cb;
-    size_t cnt = a.bytes - off < cb ? a.bytes - off : cb;
-    uint8_t* dst = reinterpret_cast<uint8_t*>(c.arena[d] + a.off_ring + ((size_t)r * a.cells + pos) * cb);
-    copy_tile<uint8_t, false>(dst, src + off, cnt);
+    if (!__syncthreads_and(ok)) return;
+#pragma unroll 1
+    for (int b = 0; b < B; b++) {
+      uint32_t i = i0 + (uint32_t)b * gridDim.x;
+      if (i >= a.ncells) break;
+      uint32_t pos = (a.first_cell + i) % (uint32_t)a.cells;
+      size_t off = (size_t)i * cb;
+      size_t cnt = a.bytes - off < cb ? a.bytes - off : cb;
+      copy_tile<uint8_t, false>(reinterpret_cast<uint8_t*>(c.arena[d] + a.off_ring + ((size_t)r * a.cells + pos) * cb), src + off, cnt);
+    }
     __syncthreads();
-    if (threadIdx.x == 0)
-      st_release_sys(reinterpret_cast<uint32_t*>(c.arena[d] + a.off_ready) + (size_t)r * kMaxCells + pos, k + 1);
+    if (t == 0) {
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
+      for (int b = 0; b < B; b++) {
+        uint32_t i = i0 + (uint32_t)b * gridDim.x;
+        if (i >= a.ncells) break;
+        uint32_t k = a.first_cell + i;
+        st_relaxed_sys(reinterpret_cast<uint32_t*>(c.arena[d] + a.off_ready) + (size_t)r * kMaxCells + k % (uint32_t)a.cells, k + 1);
+      }
+    }
   }
 }
 

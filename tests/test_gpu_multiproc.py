@@ -326,7 +326,9 @@ def test_broadcast_all_gpus(raw_world):
     is bound (unicast pushes otherwise); odd byte counts exercise the sub-vector tail."""
     actors, W = raw_world
     for root in (0, W - 1):
-        for nbytes in (1000, 100_003, 3_000_000, 20_000_001):  # the last one spans several 8 MiB pieces
+        # 20,000,001 spans several 8 MiB pieces; the 16-byte multiples >= 4 MiB take the round-pipelined paths
+        # (scatter + multicast allgather with a multicast object and W > 2, pipelined unicast pushes otherwise)
+        for nbytes in (1000, 100_003, 3_000_000, 20_000_001, 6 << 20, (24 << 20) + 4096):
             outs = get([a.broadcast.remote(nbytes, root) for a in actors])
             want = torch.randint(0, 255, (nbytes,), dtype=torch.uint8, generator=torch.Generator().manual_seed(77 + root))
             for r in range(W):

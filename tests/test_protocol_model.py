@@ -298,18 +298,36 @@ def test_ll_and_round_pipelined_kernels_between_asymmetric_ops():
 # carries flag value k+1; the sender may reuse a position only after the receiver acked its
 # previous occupant.  Blocks of a kernel take cells i, i+grid, ...
 # ---------------------------------------------------------------------------------------------
+SEND_BATCH = 4   # csrc/byte_kernels.cuh kSendBatch: cells a sender block publishes per release fence
+
+
 def _run_ring(rng, cells, messages, send_grid, recv_grid, recv_bias):
     ready, ack, ring = [0] * cells, [0] * cells, [None] * cells
     unread = [False] * cells
-    # build per-block work lists for the whole message sequence, kernel by kernel
-    def kernels(grid):
+    # per-block work lists for the whole message sequence, kernel by kernel.  A sender block takes
+    # SEND_BATCH cells per pass (stride grid), waits for the acks of ALL of them, copies, then raises
+    # their ready flags together; the host caps the sender grid at cells // SEND_BATCH so that one pass
+    # over the grid fits in the ring.  A receiver block takes one cell at a time.
+    def send_kernels(grid):
+        out, first = [], 0
+        for n in messages:
+            g = max(1, min((n + SEND_BATCH - 1) // SEND_BATCH, grid, max(1, cells // SEND_BATCH)))
+            per_block = []
+            for b in range(g):
+                mine = [first + i for i in range(b, n, g)]
+                per_block.append([mine[p:p + SEND_BATCH] for p in range(0, len(mine), SEND_BATCH)])
+            out.append(per_block)
+            first += n
+        return out
+
+    def recv_kernels(grid):
         out, first = [], 0
         for n in messages:
             g = min(n, grid, cells)
             out.append([[first + i for i in range(b, n, g)] for b in range(g)])
             first += n
         return out
-    S, R = kernels(send_grid), kernels(recv_grid)
+    S, R = send_kernels(send_grid), recv_kernels(recv_grid)
     si = ri = 0
     spc, rpc = [0] * len(S[0]), [0] * len(R[0])
     got = []
@@ -317,10 +335,8 @@ def _run_ring(rng, cells, messages, send_grid, recv_grid, recv_bias):
         cands = []
         if si < len(S):
             for b, lst in enumerate(S[si]):
-                if spc[b] < len(lst):
-                    k = lst[spc[b]]
-                    if k < cells or ack[k % cells] >= k + 1 - cells:
-                        cands.append(("s", b))
+                if spc[b] < len(lst) and all(k < cells or ack[k % cells] >= k + 1 - cells for k in lst[spc[b]]):
+                    cands.append(("s", b))
         if ri < len(R):
             for b, lst in enumerate(R[ri]):
                 if rpc[b] < len(lst) and ready[lst[rpc[b]] % cells] >= lst[rpc[b]] + 1:
@@ -328,10 +344,10 @@ def _run_ring(rng, cells, messages, send_grid, recv_grid, recv_bias):
         assert cands, "p2p ring deadlock"
         side, b = rng.choices(cands, weights=[recv_bias if c[0] == "r" else 1.0 for c in cands])[0]
         if side == "s":
-            k = S[si][b][spc[b]]
-            pos = k % cells
-            assert not unread[pos], f"cell {k} overwrites ring position {pos} before it was consumed"
-            ring[pos], unread[pos], ready[pos] = k, True, k + 1
+            for k in S[si][b][spc[b]]:
+                pos = k % cells
+                assert not unread[pos], f"cell {k} overwrites ring position {pos} before it was consumed"
+                ring[pos], unread[pos], ready[pos] = k, True, k + 1
             spc[b] += 1
             if all(spc[x] >= len(S[si][x]) for x in range(len(S[si]))):
                 si += 1
