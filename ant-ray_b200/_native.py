@@ -85,6 +85,9 @@ SYMBOLS = {
     "b200c_comm_seq": (c_uint64, [c_void_p]),
     "b200c_comm_symmetric_base": (c_void_p, [c_void_p]),
     "b200c_comm_symmetric_bytes": (c_uint64, [c_void_p]),
+    "b200c_pool_bind": (c_int, [c_void_p]),
+    "b200c_pool_malloc": (c_void_p, [c_size_t, c_int, c_void_p]),
+    "b200c_pool_free": (None, [c_void_p, c_size_t, c_int, c_void_p]),
     "b200c_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
     "b200c_allreduce_scaled": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_float, c_int, c_void_p]),
     "b200c_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),

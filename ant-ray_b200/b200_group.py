@@ -228,6 +228,24 @@ class PeerMemoryComm:
         raw = torch.as_tensor(_Holder(), device=torch.device("cuda", self.device))
         return raw.view(dtype).view(shape)
 
+    def symmetric_pool(self):
+        """A torch.cuda.MemPool backed by this communicator's symmetric region: tensors allocated under
+        `torch.cuda.use_mem_pool(pool)` — including DistributedDataParallel's gradient buckets when the model is
+        wrapped inside the context — are peer-mapped and multicast-bound, so in-place collectives on them run
+        zero-copy.  Every rank must allocate the same sequence of sizes inside the pool (offsets are matched
+        across ranks; a divergence is reported as a mismatch by the collective, not silently reduced).
+        One communicator per process can back the pool at a time."""
+        import torch
+
+        if int(self.lib.b200c_comm_symmetric_bytes(self._h())) == 0:
+            raise RuntimeError("the communicator has no symmetric region: set config.symmetric_bytes / B200COLL_SYMMETRIC_MB")
+        N.check(self.lib.b200c_pool_bind(self._h()))
+        if getattr(self, "_pool", None) is None:
+            alloc = torch.cuda.memory.CUDAPluggableAllocator(N.library_path(), "b200c_pool_malloc", "b200c_pool_free")
+            self._pool_allocator = alloc
+            self._pool = torch.cuda.MemPool(alloc.allocator())
+        return self._pool
+
     def _h(self):
         if self.handle is None:
             raise RuntimeError("B200 communicator has been destroyed.")

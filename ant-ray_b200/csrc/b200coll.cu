@@ -162,6 +162,15 @@ struct b200c_comm {
 
 static size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// symmetric pool state (see b200c_pool_bind)
+struct PoolBlock { size_t off, len; };
+static std::mutex g_pool_mu;
+static b200c_comm* g_pool_comm = nullptr;
+static PoolBlock g_pool_free[4096];
+static int g_pool_nfree = 0;
+constexpr size_t kPoolGran = 2ull << 20;
+
+
 extern "C" int b200c_version(void) { return B200C_VERSION; }
 extern "C" const char* b200c_last_error(void) { return g_err; }
 extern "C" const char* b200c_status_string(int s) {
@@ -515,6 +524,7 @@ extern "C" int b200c_comm_destroy(b200c_comm_t* c) {
   if (c->destroyed) return B200C_OK;
   c->destroyed = true;
   c->ready = false;
+  { std::lock_guard<std::mutex> lk(g_pool_mu); if (g_pool_comm == c) { g_pool_comm = nullptr; g_pool_nfree = 0; } }
   if (c->status_host) c->status_host->abort_flag = 1;
   DeviceGuard g(c->device);
   cudaDeviceSynchronize();
@@ -573,6 +583,67 @@ extern "C" int b200c_comm_has_multicast(const b200c_comm_t* c) { return c && c->
 extern "C" uint64_t b200c_comm_seq(const b200c_comm_t* c) { return c ? c->seq : 0; }
 extern "C" void* b200c_comm_symmetric_base(b200c_comm_t* c) { return c && c->sym_bytes ? c->arena[c->rank] + c->off_sym : nullptr; }
 extern "C" uint64_t b200c_comm_symmetric_bytes(const b200c_comm_t* c) { return c ? c->sym_bytes : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// Symmetric pool: a torch.cuda.MemPool (CUDAPluggableAllocator) whose segments are carved out of one
+// communicator's symmetric region, so ordinary torch tensors (and DDP's gradient buckets) allocated
+// under `torch.cuda.use_mem_pool(pool)` are peer-mapped and multicast-bound: collectives on them take
+// the zero-copy paths.  The allocator is deterministic (first fit over a sorted free list, 2 MiB
+// granules): ranks that perform the same allocation sequence get the same offsets, which is what the
+// symmetric paths require — and what b200c_allreduce verifies through the op signature (the offset is
+// part of it), so a divergence is reported as EMISMATCH instead of reducing unrelated memory.
+// ------------------------------------------------------------------------------------------------
+
+extern "C" int b200c_pool_bind(b200c_comm_t* c) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (!c) { g_pool_comm = nullptr; g_pool_nfree = 0; return B200C_OK; }
+  if (c->destroyed || !c->sym_bytes) return fail(B200C_ESTATE, "communicator has no symmetric region (config.symmetric_bytes)");
+  g_pool_comm = c;
+  g_pool_free[0] = PoolBlock{0, c->sym_bytes / kPoolGran * kPoolGran};
+  g_pool_nfree = 1;
+  return B200C_OK;
+}
+extern "C" void* b200c_pool_malloc(size_t size, int device, void* stream) {
+  (void)stream;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  b200c_comm* c = g_pool_comm;
+  if (!c || c->destroyed || device != c->device || size == 0) return nullptr;
+  size_t need = round_up(size, kPoolGran);
+  for (int i = 0; i < g_pool_nfree; i++) {
+    if (g_pool_free[i].len < need) continue;
+    size_t off = g_pool_free[i].off;
+    g_pool_free[i].off += need;
+    g_pool_free[i].len -= need;
+    if (g_pool_free[i].len == 0) { for (int j = i; j + 1 < g_pool_nfree; j++) g_pool_free[j] = g_pool_free[j + 1]; g_pool_nfree--; }
+    return c->arena[c->rank] + c->off_sym + off;
+  }
+  return nullptr;  // torch reports the out-of-memory condition
+}
+extern "C" void b200c_pool_free(void* ptr, size_t size, int device, void* stream) {
+  (void)device; (void)stream;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  b200c_comm* c = g_pool_comm;
+  if (!c || !ptr) return;
+  char* base = c->arena[c->rank] + c->off_sym;
+  if ((char*)ptr < base || (char*)ptr >= base + c->sym_bytes) return;
+  size_t off = (size_t)((char*)ptr - base), len = round_up(size, kPoolGran);
+  int i = 0;
+  while (i < g_pool_nfree && g_pool_free[i].off < off) i++;
+  if (g_pool_nfree >= 4095) return;  // cannot track it: leak the block rather than corrupt the list
+  for (int j = g_pool_nfree; j > i; j--) g_pool_free[j] = g_pool_free[j - 1];
+  g_pool_free[i] = PoolBlock{off, len};
+  g_pool_nfree++;
+  if (i + 1 < g_pool_nfree && g_pool_free[i].off + g_pool_free[i].len == g_pool_free[i + 1].off) {
+    g_pool_free[i].len += g_pool_free[i + 1].len;
+    for (int j = i + 1; j + 1 < g_pool_nfree; j++) g_pool_free[j] = g_pool_free[j + 1];
+    g_pool_nfree--;
+  }
+  if (i > 0 && g_pool_free[i - 1].off + g_pool_free[i - 1].len == g_pool_free[i].off) {
+    g_pool_free[i - 1].len += g_pool_free[i].len;
+    for (int j = i; j + 1 < g_pool_nfree; j++) g_pool_free[j] = g_pool_free[j + 1];
+    g_pool_nfree--;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // launch planning
@@ -793,7 +864,8 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
       }
     }
     a.n = n;
-    a.sig = make_sig(OPC_ALLREDUCE, dtype * 16 + wire, op, n, -1, al * 4 + (sym ? 1 : 0) + (pipe ? 2 : 0));
+    // a symmetric buffer must sit at the same arena offset on every rank: the offset is part of the signature
+    a.sig = make_sig(OPC_ALLREDUCE, dtype * 16 + wire, op, n, sym ? (int)((a.sym_off >> 4) & 0x3fffffff) : -1, al * 4 + (sym ? 1 : 0) + (pipe ? 2 : 0));
     if (al == B200C_ALGO_NVLS) {
       if (dtype == B200C_FLOAT32 && wire == B200C_FLOAT32) launch_nvls<float, float>(a, grid, s, pipe);
       else if (dtype == B200C_BFLOAT16) launch_nvls<bf16_t, bf16_t>(a, grid, s, pipe);

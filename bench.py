@@ -3,11 +3,22 @@
 
 Metric (BASELINE.json): "allreduce bus GB/s vs msg size; Ray Train ResNet-50 img/s at 1/2/4/8 B200".
   value / e2e        ResNet-50 DDP synthetic-image training throughput (whole job, weak scaling),
-                     gradients reduced by the fused peer-memory hook (ant_ray_b200.ddp_hook);
-  allreduce_sweep    bus GB/s vs message size, ours next to stock NCCL on the same processes
-                     (N >= 2), or two loopback ranks on the one GPU (N = 1);
+                     gradients reduced by the fused peer-memory hook (ant_ray_b200.ddp_hook); e2e copies
+                     every step's batch from pinned host memory (side stream, double-buffered) and reads
+                     the step's loss back;
+  allreduce_sweep    bus GB/s vs message size: ours on plain torch tensors, ours on tensors from the
+                     communicator's symmetric pool (zero-copy NVLS), stock NCCL — same processes, same
+                     sizes (N >= 2); two loopback ranks on the one GPU (N = 1);
+  collectives        broadcast / allgather / reducescatter next to the reference's NCCL call pattern;
+  p2p                2-rank B200Communicator.send/recv in the shape of the reference's compiled-graph GPU
+                     microbenchmark (fp16, 100,000 bytes) + a size sweep, next to torch.distributed NCCL;
+  comm_bound         the same training step at the reference harness's default batch 32, fp32 and bf16
+                     gradient wire, ours next to stock NCCL DDP (where the collective is not hidden);
+  parity             (N >= 2, untimed) every algorithm of the multi-GPU path checked against the NCCL
+                     result of the same seeded buffers: integers bit-exact, fp32 max relative error,
+                     identical bits on all ranks; hooked-DDP gradients against stock DDP;
   roofline           the dominant kernel of OUR path (the fused gradient reduction), timed live with
-                     CUDA events on the stream it is launched on;
+                     CUDA events on the stream it is launched on, back to back;
   cpu_baseline       the reference's CPU path (torch DDP over gloo, which is what Ray Train's
                      _TorchBackend selects without GPUs: train/torch/config.py:167-176) on the
                      box's host cores, bounded sample, N = 1 only.
@@ -33,6 +44,10 @@ if ROOT not in sys.path:
 RESNET50_PARAMS = 25_557_032
 NVLINK_PEAK_MEASURED = 770.0   # GB/s per direction per GPU, peer copy (B200_PROFILING.md)
 NVLINK_PEAK_NOMINAL = 900.0
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the N = 1 roofline kernel, from the committed
+# `ncu --set full` capture (profiles/r02_ncu_full_1gpu_details.txt: k_local_scale<float, bf16_t>, 30 MiB bucket):
+# 31.47 MB read; the 31.46 MB written are still dirty in the 126 MB L2 when the kernel ends (ncu: 0.00 MB)
+NCU_TRAFFIC_LOCAL_SCALE_30MIB = 31_468_544 + 4_096
 
 
 def log(msg):
@@ -51,6 +66,9 @@ def parse():
     p.add_argument("--no-sweep", action="store_true")
     p.add_argument("--no-nccl-ddp", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-parity", action="store_true")
+    p.add_argument("--no-p2p", action="store_true")
+    p.add_argument("--no-comm-bound", action="store_true")
     p.add_argument("--sweep-max-bytes", type=int, default=int(os.environ.get("BENCH_SWEEP_MAX", 1 << 30)))
     return p.parse_args()
 
@@ -138,43 +156,84 @@ def make_step(model, opt, use_autocast, device):
     return step
 
 
-def timed_steps(step, x, y, steps, dist, world, pinned=None):
-    """Time exactly `steps` steps on the device, barrier + synchronize on both sides, max over ranks.
-    With `pinned` = (x_host, y_host) every step copies its inputs from pinned host memory and reads the
-    loss back (the end-to-end number)."""
+def fence(dist, world):
     import torch
 
-    def fence():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(value, dist, world):
+    import torch
+
+    if world > 1:
+        t = torch.tensor([value], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+    return value
+
+
+def timed_steps(step, x, y, steps, dist, world):
+    """Device-resident inputs: exactly `steps` steps between two fences, CUDA events, max over ranks."""
+    import torch
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fence()
+    fence(dist, world)
     t0 = time.time()
     e0.record()
-    last = None
     for _ in range(steps):
-        if pinned is not None:
-            x.copy_(pinned[0], non_blocking=True)
-            y.copy_(pinned[1], non_blocking=True)
-        loss = step(x, y)
-        if pinned is not None:
-            last = loss.item()
+        step(x, y)
     e1.record()
-    fence()
+    fence(dist, world)
     t1 = time.time()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
-    return ms, (t0, t1), last
+    return max_over_ranks(e0.elapsed_time(e1), dist, world), (t0, t1)
+
+
+def timed_steps_e2e(step, x_host, y_host, steps, dist, world, device):
+    """End to end through the public API: every step's batch comes from pinned host memory (H2D inside the
+    timed region, on a side stream, double-buffered so the copy of step i+1 overlaps step i) and every
+    step's loss goes back to pinned host memory (D2H inside the timed region, asynchronous; the host reads
+    the values after the final fence instead of stalling the GPU queue once per step)."""
+    import torch
+
+    copy_stream = torch.cuda.Stream(device=device)
+    cur_stream = torch.cuda.current_stream(device)
+    bufs = [(torch.empty_like(x_host, device=device), torch.empty_like(y_host, device=device)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.empty(steps, dtype=torch.float32).pin_memory()
+
+    def prefetch(slot, first=False):
+        with torch.cuda.stream(copy_stream):
+            if not first:
+                copy_stream.wait_event(consumed[slot])   # the step that read this slot has finished
+            bufs[slot][0].copy_(x_host, non_blocking=True)
+            bufs[slot][1].copy_(y_host, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence(dist, world)
+    t0 = time.time()
+    e0.record()
+    prefetch(0, first=True)
+    for i in range(steps):
+        slot = i & 1
+        cur_stream.wait_event(ready[slot])
+        if i + 1 < steps:
+            prefetch(slot ^ 1, first=(i == 0))
+        loss = step(bufs[slot][0], bufs[slot][1])
+        consumed[slot].record(cur_stream)
+        loss_host[i].copy_(loss.detach().float(), non_blocking=True)
+    e1.record()
+    fence(dist, world)
+    t1 = time.time()
+    return max_over_ranks(e0.elapsed_time(e1), dist, world), (t0, t1), float(loss_host[-1])
 
 
 # ------------------------------------------------------------------------------------------------
-# allreduce sweep: ours vs NCCL, same processes, same buffers
+# collective timing helpers
 # ------------------------------------------------------------------------------------------------
 def sweep_sizes(max_bytes):
     s, out = 1024, []
@@ -195,10 +254,7 @@ def time_collective(fn, bufs, iters, dist, world, rounds=2):
     for _ in range(rounds):
         for i in range(min(5, iters)):
             fn(bufs[i % len(bufs)])
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        fence(dist, world)
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
         for i, (e0, e1) in enumerate(evs):
             e0.record()
@@ -206,18 +262,35 @@ def time_collective(fn, bufs, iters, dist, world, rounds=2):
             e1.record()
         torch.cuda.synchronize()
         ts = sorted(e0.elapsed_time(e1) * 1e3 for e0, e1 in evs)
-        us = ts[len(ts) // 2]
-        if world > 1:
-            t = torch.tensor([us], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            us = t.item()
+        us = max_over_ranks(ts[len(ts) // 2], dist, world)
+        best = us if best is None else min(best, us)
+    return best
+
+
+def time_back_to_back(fn, bufs, iters, dist, world, rounds=3):
+    """Microseconds per call over a back-to-back loop of `iters` launches (one event pair around the loop,
+    so launch latency is hidden behind the previous kernel, as it is inside a training step), best of `rounds`."""
+    import torch
+
+    best = None
+    for _ in range(rounds):
+        for i in range(3):
+            fn(bufs[i % len(bufs)])
+        fence(dist, world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(bufs[i % len(bufs)])
+        e1.record()
+        torch.cuda.synchronize()
+        us = max_over_ranks(e0.elapsed_time(e1) * 1e3 / iters, dist, world)
         best = us if best is None else min(best, us)
     return best
 
 
 def time_fused_bucket(comm, dist, world, wire):
     """The fused gradient kernel alone (full grid, nothing else on the GPU) on ResNet-50's largest bucket
-    (30 MiB fp32), in place, rotating over 8 buckets (240 MiB > L2).  Microseconds per launch."""
+    (30 MiB fp32), in place, rotating over 8 buckets (240 MiB > L2).  Microseconds per launch, back to back."""
     import torch
 
     from ant_ray_b200 import _native as N
@@ -225,18 +298,20 @@ def time_fused_bucket(comm, dist, world, wire):
     n = 30 << 18
     wire_code = {"bf16": N.BFLOAT16, "fp16": N.FLOAT16, "fp32": N.FLOAT32}[wire]
     bufs = [torch.randn(n, device="cuda") for _ in range(8)]
-    us = time_collective(lambda b: comm.allreduce_scaled(b.data_ptr(), b.data_ptr(), n, N.FLOAT32, wire_code, 1.0 / world, N.ALGO_AUTO),
-                         bufs, 40, dist, world)
+    us = time_back_to_back(lambda b: comm.allreduce_scaled(b.data_ptr(), b.data_ptr(), n, N.FLOAT32, wire_code, 1.0 / world, N.ALGO_AUTO),
+                           bufs, 40, dist, world)
     return us, n
 
 
 def run_sweep_multi(comm, dist, world, max_bytes):
-    """N >= 2: in-place fp32 SUM allreduce of plain torch tensors, ours (AUTO) vs torch c10d NCCL."""
+    """N >= 2: in-place fp32 SUM allreduce, ours (AUTO) on plain torch tensors, ours on a tensor from the
+    communicator's symmetric pool (same call, zero-copy NVLS), and torch c10d NCCL on the plain tensors."""
     import torch
 
     from ant_ray_b200 import _native as N
 
     rows = []
+    sym_cap = int(comm.lib.b200c_comm_symmetric_bytes(comm.handle))
     for size in sweep_sizes(max_bytes):
         n = size // 4
         nbuf = max(1, min(16, (256 << 20) // size))  # rotate buffers so small sizes are not L2-resident replays
@@ -245,9 +320,65 @@ def run_sweep_multi(comm, dist, world, max_bytes):
         ours = time_collective(lambda b: comm.allreduce(b.data_ptr(), b.data_ptr(), n, N.FLOAT32, N.SUM, N.ALGO_AUTO), bufs, iters, dist, world)
         nccl = time_collective(lambda b: dist.all_reduce(b), bufs, iters, dist, world)
         k = 2 * (world - 1) / world
-        rows.append({"bytes": size, "b200_us": round(ours, 2), "nccl_us": round(nccl, 2),
-                     "b200_busbw": round(size / ours / 1e3 * k, 2), "nccl_busbw": round(size / nccl / 1e3 * k, 2)})
+        row = {"bytes": size, "b200_us": round(ours, 2), "nccl_us": round(nccl, 2),
+               "b200_busbw": round(size / ours / 1e3 * k, 2), "nccl_busbw": round(size / nccl / 1e3 * k, 2)}
+        if comm.multicast and size <= sym_cap and size >= (1 << 20) and size % 16 == 0:
+            nsym = max(1, min(nbuf, sym_cap // size))
+            sbufs = [comm.symmetric_tensor((n,), torch.float32, byte_offset=i * size) for i in range(nsym)]
+            for b in sbufs:
+                b.fill_(1.0)
+            sym = time_collective(lambda b: comm.allreduce(b.data_ptr(), b.data_ptr(), n, N.FLOAT32, N.SUM, N.ALGO_AUTO), sbufs, iters, dist, world)
+            row["b200_sym_us"], row["b200_sym_busbw"] = round(sym, 2), round(size / sym / 1e3 * k, 2)
+        rows.append(row)
         del bufs
+    return rows
+
+
+def run_other_collectives(comm, dist, world):
+    """broadcast / allgather / reducescatter next to the reference's call pattern on NCCL (allgather into a flat
+    buffer + W copies, W copies + reducescatter: nccl_collective_group.py:278-296, 319-337)."""
+    import torch
+
+    from ant_ray_b200 import _native as N
+
+    rows = []
+    for size in (1 << 20, 64 << 20):
+        n = size // 4
+        nbuf = max(1, min(8, (256 << 20) // size))
+        bufs = [torch.ones(n, device="cuda") for _ in range(nbuf)]
+        iters = 50 if size <= (1 << 20) else 10
+        ours = time_collective(lambda b: comm.broadcast(b.data_ptr(), n, N.FLOAT32, 0), bufs, iters, dist, world)
+        ref = time_collective(lambda b: dist.broadcast(b, 0), bufs, iters, dist, world)
+        rows.append({"op": "broadcast", "bytes": size, "b200_us": round(ours, 2), "nccl_us": round(ref, 2),
+                     "b200_busbw": round(size / ours / 1e3, 1), "nccl_busbw": round(size / ref / 1e3, 1)})
+        per = size // world // 4 * 4
+        m = per // 4
+        outs = [torch.empty(m, device="cuda") for _ in range(world)]
+        flat = torch.empty(m * world, device="cuda")
+        src = torch.ones(m, device="cuda")
+        ptrs = [o.data_ptr() for o in outs]
+        kf = (world - 1) / world
+        ours = time_collective(lambda b: comm.allgather(src.data_ptr(), ptrs, m, N.FLOAT32), [None], iters, dist, world)
+
+        def ref_ag(_):
+            dist.all_gather_into_tensor(flat, src)
+            for j in range(world):
+                outs[j].copy_(flat[j * m:(j + 1) * m])
+
+        ref = time_collective(ref_ag, [None], iters, dist, world)
+        rows.append({"op": "allgather", "bytes_total": per * world, "b200_us": round(ours, 2), "nccl_ref_us": round(ref, 2),
+                     "b200_busbw": round(per * world / ours / 1e3 * kf, 1), "nccl_ref_busbw": round(per * world / ref / 1e3 * kf, 1)})
+        o = torch.empty(m, device="cuda")
+        ours = time_collective(lambda b: comm.reducescatter(ptrs, o.data_ptr(), m, N.FLOAT32, N.SUM), [None], iters, dist, world)
+
+        def ref_rs(_):
+            for j in range(world):
+                flat[j * m:(j + 1) * m].copy_(outs[j])
+            dist.reduce_scatter_tensor(o, flat)
+
+        ref = time_collective(ref_rs, [None], iters, dist, world)
+        rows.append({"op": "reducescatter", "bytes_total": per * world, "b200_us": round(ours, 2), "nccl_ref_us": round(ref, 2),
+                     "b200_busbw": round(per * world / ours / 1e3 * kf, 1), "nccl_ref_busbw": round(per * world / ref / 1e3 * kf, 1)})
     return rows
 
 
@@ -284,6 +415,310 @@ def run_sweep_loopback(max_bytes):
         world.check()
     finally:
         world.destroy()
+    return rows
+
+
+# ------------------------------------------------------------------------------------------------
+# p2p: the reference's compiled-graph GPU microbenchmark shape
+# (release/microbenchmark/experimental/compiled_graph_gpu_microbenchmark.py:71-112, 441-451)
+# ------------------------------------------------------------------------------------------------
+def run_p2p(dist, world, rank, device):
+    """Ranks 0 (sender) and 1 (receiver).  `exec`: the reference's NcclWorker._run body — allocate, send / recv,
+    torch.cuda.synchronize — per message, fp16, 100,000 bytes, ours through B200Communicator.send/recv and NCCL
+    through torch.distributed.send/recv.  `sweep`: device-timed GB/s for larger messages."""
+    import torch
+
+    from ant_ray_b200.communicator import B200Communicator
+
+    ids = [B200Communicator.generate_communicator_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    comm = B200Communicator(world, ids[0], rank, list(range(world)), torch.cuda.current_stream(), False)
+    alloc = lambda shape, dtype: torch.empty(shape, dtype=dtype, device=device)  # noqa: E731
+    out = {"harness": "compiled_graph_gpu_microbenchmark.py NcclWorker.do_send_recv: alloc + send/recv + cuda synchronize per message"}
+    try:
+        n = 100_000 // 2
+
+        def ours():
+            if rank == 0:
+                comm.send(torch.ones(n, dtype=torch.float16, device=device), 1)
+            elif rank == 1:
+                comm.recv((n,), torch.float16, 0, alloc)
+            torch.cuda.synchronize()
+
+        def nccl():
+            if rank == 0:
+                dist.send(torch.ones(n, dtype=torch.float16, device=device), 1)
+            elif rank == 1:
+                dist.recv(torch.empty(n, dtype=torch.float16, device=device), 0)
+            torch.cuda.synchronize()
+
+        for name, fn in (("b200", ours), ("nccl", nccl)):
+            for _ in range(20):
+                fn()
+            fence(dist, world)
+            iters = 300
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                fn()
+            us = (time.perf_counter() - t0) / iters * 1e6
+            out[f"{name}_100kB_fp16_us_per_msg"] = round(max_over_ranks(us if rank < 2 else 0.0, dist, world), 2)
+        rows = []
+        for size in (1 << 20, 16 << 20, 64 << 20, 256 << 20):
+            m = size // 2
+            nbuf = max(1, min(4, (256 << 20) // size))
+            bufs = [torch.ones(m, dtype=torch.float16, device=device) for _ in range(nbuf)]
+            from ant_ray_b200.b200_group import TensorView
+
+            def o(b):
+                v = TensorView(b)
+                if rank == 0:
+                    comm._comm.send(v.ptr, size, 1)
+                elif rank == 1:
+                    comm._comm.recv(v.ptr, size, 0)
+
+            def r(b):
+                if rank == 0:
+                    dist.send(b, 1)
+                elif rank == 1:
+                    dist.recv(b, 0)
+
+            iters = 30 if size <= (16 << 20) else 10
+            a = time_back_to_back(o, bufs, iters, dist, world, rounds=2)
+            b = time_back_to_back(r, bufs, iters, dist, world, rounds=2)
+            rows.append({"bytes": size, "b200_us": round(a, 2), "nccl_us": round(b, 2), "b200_gbps": round(size / a / 1e3, 1), "nccl_gbps": round(size / b / 1e3, 1)})
+        out["sweep"] = rows
+        comm.check()
+    finally:
+        comm.destroy()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# parity: the multi-GPU path against the NCCL result of the same seeded buffers (untimed)
+# ------------------------------------------------------------------------------------------------
+def run_parity(comm, dist, world, rank, device, wire):
+    """SURVEY.md 8(d) inputs: rank r draws from manual_seed(1234 + r).  For every algorithm of the path:
+    int32 SUM bit-exact against ncclAllReduce of the same buffers (nccl_collective_group.py:181-188), fp32 SUM
+    max |ours - nccl| / max |nccl|, and identical bits on every rank (checksum compared across ranks)."""
+    import torch
+
+    from ant_ray_b200 import _native as N
+
+    res = {}
+    g = torch.Generator().manual_seed(1234 + rank)
+
+    def same_everywhere(t):
+        s = t.view(torch.uint8).to(torch.int64).sum() if t.dtype != torch.int32 else t.to(torch.int64).sum()
+        s2 = (t.view(torch.int32).to(torch.int64) * torch.arange(1, t.view(torch.int32).numel() + 1, device=t.device) % 1000003).sum()
+        mine = torch.stack([s, s2])
+        allv = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        return all(bool(torch.equal(v, allv[0])) for v in allv)
+
+    def check_allreduce(name, algo, n, use_int=True, sym=False):
+        entry = {}
+        xf = torch.randn(n, generator=g).to(device)
+        ref = xf.clone()
+        dist.all_reduce(ref)
+        if sym:
+            cur = comm.symmetric_tensor((n,), torch.float32)
+            cur.copy_(xf)
+        else:
+            cur = xf.clone()
+        comm.allreduce(cur.data_ptr(), cur.data_ptr(), n, N.FLOAT32, N.SUM, algo)
+        torch.cuda.synchronize()
+        comm.check()
+        entry["fp32_max_rel_err"] = float(((cur - ref).abs().max() / ref.abs().max()).item())
+        entry["identical_on_all_ranks"] = same_everywhere(cur)
+        if use_int:
+            xi = torch.randint(-(2**15), 2**15, (n,), generator=g, dtype=torch.int32).to(device)
+            refi = xi.clone()
+            dist.all_reduce(refi)
+            comm.allreduce(xi.data_ptr(), xi.data_ptr(), n, N.INT32, N.SUM, algo)
+            torch.cuda.synchronize()
+            comm.check()
+            entry["int32_bit_exact"] = bool(torch.equal(xi, refi))
+        entry["ok"] = entry["fp32_max_rel_err"] <= 1e-5 and entry["identical_on_all_ranks"] and entry.get("int32_bit_exact", True)
+        res[name] = entry
+
+    check_allreduce("ll", N.ALGO_LL, 4099)
+    check_allreduce("oneshot", N.ALGO_ONESHOT, 100_003)
+    check_allreduce("twoshot", N.ALGO_TWOSHOT, 3_000_001)
+    check_allreduce("auto_1KiB", N.ALGO_AUTO, 256)
+    check_allreduce("auto_64MiB", N.ALGO_AUTO, 16 << 20)
+    if comm.multicast:
+        check_allreduce("nvls_staged", N.ALGO_NVLS, 3_000_001, use_int=False)
+        check_allreduce("nvls_rounds", N.ALGO_NVLS_PIPE, (16 << 20) + 4, use_int=False)
+        check_allreduce("nvls_symmetric", N.ALGO_NVLS, 4 << 20, use_int=False, sym=True)
+    # fused gradient mean, 16-bit wire: against the reference's own formulation (bf16_compress_hook:
+    # buffer.to(bf16).div_(W) -> allreduce -> copy back, torch default_hooks.py)
+    n = 7_500_003
+    x = torch.randn(n, generator=g).to(device)
+    ours = x.clone()
+    wcode = {"bf16": N.BFLOAT16, "fp16": N.FLOAT16, "fp32": N.FLOAT32}[wire]
+    comm.allreduce_scaled(ours.data_ptr(), ours.data_ptr(), n, N.FLOAT32, wcode, 1.0 / world, N.ALGO_AUTO)
+    wdt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[wire]
+    refc = x.to(wdt).div_(world)
+    dist.all_reduce(refc)
+    exact = x.clone()
+    dist.all_reduce(exact)
+    exact /= world
+    torch.cuda.synchronize()
+    comm.check()
+    scale = exact.abs().max()
+    e_ours, e_ref = float(((ours - exact).abs().max() / scale).item()), float(((refc.float() - exact).abs().max() / scale).item())
+    tol = {"bf16": 2 ** -7, "fp16": 2 ** -10, "fp32": 1e-5}[wire]
+    res["fused_mean_%s_wire" % wire] = {"max_rel_err_vs_fp32_mean": e_ours, "nccl_compress_hook_formulation_err": e_ref,
+                                        "identical_on_all_ranks": same_everywhere(ours), "ok": e_ours <= tol and same_everywhere(ours)}
+    # data movement: broadcast (small: root multicast / unicast; large: round-pipelined), allgather, reducescatter, p2p
+    for name, nb in (("broadcast_1MiB", 1 << 20), ("broadcast_24MiB", 24 << 20)):
+        b = torch.randint(0, 255, (nb,), generator=g, dtype=torch.uint8).to(device)
+        want = b.clone()
+        dist.broadcast(want, world - 1)
+        comm.broadcast(b.data_ptr(), nb, N.UINT8, world - 1)
+        torch.cuda.synchronize()
+        comm.check()
+        res[name] = {"bit_exact": bool(torch.equal(b, want)), "ok": bool(torch.equal(b, want))}
+    m = 300_001
+    xi = torch.randint(-1000, 1000, (m,), generator=g, dtype=torch.int32).to(device)
+    outs = [torch.zeros(m, dtype=torch.int32, device=device) for _ in range(world)]
+    refs = [torch.zeros(m, dtype=torch.int32, device=device) for _ in range(world)]
+    dist.all_gather(refs, xi)
+    comm.allgather(xi.data_ptr(), [o.data_ptr() for o in outs], m, N.INT32)
+    torch.cuda.synchronize()
+    ok = all(bool(torch.equal(a, b)) for a, b in zip(outs, refs))
+    res["allgather"] = {"bit_exact": ok, "ok": ok}
+    ins = [torch.randint(-1000, 1000, (m,), generator=g, dtype=torch.int32).to(device) for _ in range(world)]
+    o, ro = torch.zeros(m, dtype=torch.int32, device=device), torch.zeros(m, dtype=torch.int32, device=device)
+    dist.reduce_scatter(ro, [t.clone() for t in ins])
+    comm.reducescatter([t.data_ptr() for t in ins], o.data_ptr(), m, N.INT32, N.SUM)
+    torch.cuda.synchronize()
+    comm.check()
+    res["reducescatter"] = {"bit_exact": bool(torch.equal(o, ro)), "ok": bool(torch.equal(o, ro))}
+    payload = torch.randint(0, 255, (5_000_017,), generator=torch.Generator().manual_seed(99), dtype=torch.uint8).to(device)
+    got = torch.zeros_like(payload)
+    if rank == 0:
+        comm.send(payload.data_ptr(), payload.numel(), 1)
+        if world > 2:
+            comm.send_multi(payload.data_ptr(), payload.numel(), list(range(1, world)))
+    else:
+        if rank == 1:
+            comm.recv(got.data_ptr(), got.numel(), 0)
+            torch.cuda.synchronize()
+            first = bool(torch.equal(got, payload))
+            got.zero_()
+        if world > 2:
+            comm.recv_multi(got.data_ptr(), got.numel(), 0)
+    torch.cuda.synchronize()
+    comm.check()
+    flags = torch.tensor([1 if (rank == 0 or (torch.equal(got, payload) if world > 2 else True)) else 0,
+                          1 if (rank != 1 or first) else 0], device=device)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    res["send_recv"] = {"bit_exact": bool(flags[1].item()), "ok": bool(flags[1].item())}
+    if world > 2:
+        res["send_multi_%d_readers" % (world - 1)] = {"bit_exact": bool(flags[0].item()), "ok": bool(flags[0].item())}
+    return res
+
+
+def run_ddp_grad_parity(dist, world, rank, device):
+    """Register the hook on a real DistributedDataParallel model (ResNet-50, bf16 autocast) and compare every
+    parameter's .grad after a backward pass with what stock DDP produces from the SAME local gradients: the hook
+    is wrapped so that each bucket is also reduced the stock way on a copy — torch's default reducer
+    (`buffer.div_(W)`; allreduce) for the fp32 wire, bf16_compress_hook (`buffer.to(bf16).div_(W)`; allreduce;
+    copy back) for the bf16 wire (torch default_hooks.py) — before the fused kernel runs on the bucket itself.
+    Comparing two separate backward passes instead would mix in cuDNN's run-to-run nondeterminism."""
+    import torch
+    from torch.nn.parallel import DistributedDataParallel
+
+    from ant_ray_b200 import ddp_hook
+
+    out = {}
+    gen = torch.Generator().manual_seed(4321 + rank)
+    x = torch.randn(16, 3, 224, 224, generator=gen).to(device).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 1000, (16,), generator=gen).to(device)
+    for wire in ("fp32", "bf16"):
+        m = DistributedDataParallel(build_model(device), device_ids=[device], output_device=device)
+        state = ddp_hook.make_grad_state(device=device.index, wire=wire, name="parity-" + wire)
+        expected = {}
+
+        def both(st, bucket, wire=wire, expected=expected):
+            buf = bucket.buffer()
+            if wire == "fp32":
+                ref = buf.clone().div_(world)
+                dist.all_reduce(ref)
+            else:
+                ref16 = buf.to(torch.bfloat16).div_(world)
+                dist.all_reduce(ref16)
+                ref = ref16.float()
+            for p_, gview in zip(bucket.parameters(), bucket.gradients()):
+                off = gview.storage_offset() - buf.storage_offset()
+                expected[p_] = ref[off:off + gview.numel()].view_as(p_)
+            return ddp_hook.b200_allreduce_hook(st, bucket)
+
+        m.register_comm_hook(state, both)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = torch.nn.functional.cross_entropy(m(x), y)
+        loss.backward()
+        torch.cuda.synchronize()
+        state.comm.check()
+        params = [p_ for p_ in m.parameters() if p_.grad is not None]
+        num = max(float((p_.grad - expected[p_]).abs().max().item()) for p_ in params)
+        den = max(float(expected[p_].abs().max().item()) for p_ in params)
+        tol = 1e-5 if wire == "fp32" else 2 ** -6
+        out["ddp_grads_%s_wire" % wire] = {"max_rel_err_vs_stock_ddp": num / den, "n_params": len(params), "n_buckets_launches": state.launches,
+                                           "ok": num / den <= tol and len(params) == len(expected)}
+        state.comm.destroy()
+        del m
+        torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# comm-bound rows: the reference harness's default batch (release/train_tests/benchmark/config.py:16)
+# ------------------------------------------------------------------------------------------------
+def run_comm_bound(args, dist, world, device, steps=30, warmup=8):
+    import torch
+    from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+    from torch.nn.parallel import DistributedDataParallel
+
+    from ant_ray_b200 import train as b200_train
+
+    B = 32
+    rows = []
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(B, 3, 224, 224, generator=g).to(device).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 1000, (B,), generator=g).to(device)
+    for wire in ("fp32", "bf16"):
+        row = {"per_gpu_batch": B, "grad_wire": wire}
+        model = b200_train.prepare_model(build_model(device), grad_wire=wire, wrap_single=True)
+        state = model.b200_grad_state
+        opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9)
+        step = make_step(model, opt, True, device)
+        for _ in range(warmup):
+            step(x, y)
+        state.time_kernels, state.events = True, []
+        ms, _ = timed_steps(step, x, y, steps, dist, world)
+        kt = state.kernel_times_ms()
+        state.time_kernels = False
+        row["b200_images_per_sec"] = round(world * B * steps / (ms / 1e3), 1)
+        row["b200_ms_per_step"] = round(ms / steps, 3)
+        row["b200_hook_ms_per_step"] = round(sum(t for t, _ in kt) / steps, 4)
+        state.comm.destroy()
+        del model, opt, step
+        m2 = DistributedDataParallel(build_model(device), device_ids=[device], output_device=device)
+        if wire == "bf16":
+            m2.register_comm_hook(None, default_hooks.bf16_compress_hook)
+        o2 = torch.optim.SGD(m2.parameters(), lr=0.01, momentum=0.9)
+        s2 = make_step(m2, o2, True, device)
+        for _ in range(warmup):
+            s2(x, y)
+        ms2, _ = timed_steps(s2, x, y, steps, dist, world)
+        row["nccl_images_per_sec"] = round(world * B * steps / (ms2 / 1e3), 1)
+        row["nccl_ms_per_step"] = round(ms2 / steps, 3)
+        row["ratio"] = round(row["b200_images_per_sec"] / row["nccl_images_per_sec"], 4)
+        del m2, o2, s2
+        torch.cuda.empty_cache()
+        rows.append(row)
     return rows
 
 
@@ -384,13 +819,14 @@ def cpu_reference(world, batch, steps, warmup, budget_s=60.0):
 
 
 def workload_config(B, world, wire):
-    """The workload both arms report (the reference arm runs a bounded sample of it)."""
+    """The workload both arms report (the reference arm runs a bounded sample of it: its own per-worker batch
+    is what `per_gpu_batch` says on that arm's line)."""
     return {"workload": "Ray Train TorchTrainer-shaped ResNet-50 DDP step (prepare_model + gradient reduction hook), "
                         "synthetic randn(B,3,224,224), SGD momentum, bf16 autocast, fp32 grads",
             "model": "torchvision.resnet50", "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
             "grad_wire": wire, "grad_bytes_per_step": RESNET50_PARAMS * 4,
-            "l2": "per-step working set (activations of 256 images) is far larger than the 126 MB L2; "
-                  "the sweep rotates buffers totalling >= 256 MB"}
+            "l2": "per-step working set (activations of the batch) is far larger than the 126 MB L2; "
+                  "the sweeps rotate buffers totalling >= 256 MB"}
 
 
 def run_reference(args):
@@ -401,14 +837,17 @@ def run_reference(args):
     batch = int(os.environ.get("BENCH_CPU_BATCH", 16))  # bounded sample: small per-worker batch
     ips, sps, cores, done, cpu_dtype = cpu_reference(world, batch, args.steps, args.warmup, budget_s=float(os.environ.get("BENCH_CPU_BUDGET_S", 150)))
     sample = f"{world} gloo worker(s) x batch {batch}, {done} steps after <= {args.warmup} warm-up, torch DDP default reducer, {cpu_dtype}"
+    cfg = workload_config(batch, world, "fp32")   # the batch this arm really ran
+    cfg.update({"reference_path": "torch DDP default reducer over a gloo process group on the host CPUs (what "
+                                  "ray.train.torch.TorchConfig selects without GPUs, train/torch/config.py:167-176)",
+                "b200_arm_per_gpu_batch": args.batch,
+                "sample_note": "bounded sample of the b200 arm's workload: same model, step and metric, smaller per-worker batch so "
+                               "that the CPU run ends within minutes"})
     print(json.dumps({
         "impl": "reference", "metric": "resnet50_ddp_train_images_per_sec", "value": round(ips, 2), "unit": "images/s",
         "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": round(sps * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {**workload_config(args.batch, world, args.wire),
-                   "reference_path": "torch DDP default reducer over a gloo process group on the host CPUs (what "
-                                     "ray.train.torch.TorchConfig selects without GPUs, train/torch/config.py:167-176)",
-                   "sample_per_worker_batch": batch},
+        "config": cfg,
         "cpu_baseline": {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(ips, 2), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -441,6 +880,7 @@ def main():
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
     torch.backends.cudnn.benchmark = True
     N.load()
+    optional_errors = {}
 
     B = args.batch
     model = build_model(device)
@@ -449,11 +889,10 @@ def main():
     opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9)
     step = make_step(model, opt, use_autocast=True, device=device)
     g = torch.Generator().manual_seed(1234 + rank)
-    x_host = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
+    x_host = torch.randn(B, 3, 224, 224, generator=g).contiguous(memory_format=torch.channels_last).pin_memory()
     y_host = torch.randint(0, 1000, (B,), generator=g).pin_memory()
-    x = x_host.to(device, non_blocking=True).contiguous(memory_format=torch.channels_last)
+    x = x_host.to(device, non_blocking=True)
     y = y_host.to(device, non_blocking=True)
-    x_host_cl = x_host.contiguous(memory_format=torch.channels_last).pin_memory()
 
     log(f"model ready, B={B}, world={world}; warm-up")
     sampler = ClockSampler(local).start() if rank == 0 else None
@@ -466,7 +905,7 @@ def main():
     l0 = N.launch_count()
     if os.environ.get("BENCH_CUDA_PROFILER") == "1":  # ncu --profile-from-start off: capture the timed region only
         torch.cuda.profiler.start()
-    ms, win1, _ = timed_steps(step, x, y, args.steps, dist, world)
+    ms, win1 = timed_steps(step, x, y, args.steps, dist, world)
     if os.environ.get("BENCH_CUDA_PROFILER") == "1":
         torch.cuda.profiler.stop()
     launches = N.launch_count() - l0
@@ -474,14 +913,13 @@ def main():
     state.time_kernels = False
     log("timing end-to-end steps")
     # ---- end to end: inputs from pinned host memory every step, loss read back every step
-    ms_e2e, win2, last_loss = timed_steps(step, x, y, args.steps, dist, world, pinned=(x_host_cl, y_host))
+    ms_e2e, win2, last_loss = timed_steps_e2e(step, x_host, y_host, args.steps, dist, world, device)
     value = world * B * args.steps / (ms / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
 
     # ---- stock DDP reducer over NCCL on the same box (B-DDP baseline)
     nccl_ddp = None
     log("stock NCCL DDP baseline")
-    optional_errors = {}
     if not args.no_nccl_ddp:
         try:  # a failure of an optional section must not cost the headline line
             from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
@@ -494,30 +932,63 @@ def main():
             s2 = make_step(m2, o2, use_autocast=True, device=device)
             for _ in range(max(3, args.warmup)):
                 s2(x, y)
-            ms2, _, _ = timed_steps(s2, x, y, args.steps, dist, world)
+            ms2, _ = timed_steps(s2, x, y, args.steps, dist, world)
             nccl_ddp = world * B * args.steps / (ms2 / 1e3)
             del m2, o2, s2
         except Exception as e:  # noqa: BLE001
             optional_errors["nccl_ddp"] = repr(e)[:300]
+    multicast = bool(state.comm.multicast)
+    del model, opt, step
+    torch.cuda.empty_cache()
 
-    # ---- allreduce sweep
-    sweep = None
-    fused_alone = None
-    log("allreduce sweep")
-    if not args.no_sweep:
-        del model, opt, step
-        torch.cuda.empty_cache()
+    comm_bound = None
+    if world > 1 and not args.no_comm_bound:
+        log("comm-bound rows (batch 32)")
         try:
-            if world > 1:
-                from ant_ray_b200.b200_group import PeerMemoryComm, next_comm_key
+            comm_bound = run_comm_bound(args, dist, world, device)
+        except Exception as e:  # noqa: BLE001
+            optional_errors["comm_bound"] = repr(e)[:300]
 
-                sweep_comm = PeerMemoryComm(world, rank, next_comm_key("bench-sweep"), local)  # default (full-size) grid
+    # ---- collectives: parity, p2p, sweeps
+    sweep = collectives = p2p = parity = None
+    fused_alone = None
+    if world > 1:
+        from ant_ray_b200.b200_group import PeerMemoryComm, make_config, next_comm_key
+
+        sym_bytes = min(args.sweep_max_bytes, 1 << 30)
+        sweep_comm = PeerMemoryComm(world, rank, next_comm_key("bench-sweep"), local, None, make_config(symmetric_bytes=sym_bytes))
+        if not args.no_parity:
+            log("parity block")
+            try:
+                parity = run_parity(sweep_comm, dist, world, rank, device, args.wire)
+                parity.update(run_ddp_grad_parity(dist, world, rank, device))
+                parity["all_ok"] = all(v.get("ok", False) for v in parity.values() if isinstance(v, dict))
+            except Exception as e:  # noqa: BLE001
+                optional_errors["parity"] = repr(e)[:400]
+        if not args.no_p2p:
+            log("p2p block")
+            try:
+                p2p = run_p2p(dist, world, rank, device)
+            except Exception as e:  # noqa: BLE001
+                optional_errors["p2p"] = repr(e)[:300]
+        if not args.no_sweep:
+            log("allreduce sweep")
+            try:
                 fused_alone = time_fused_bucket(sweep_comm, dist, world, args.wire)
                 sweep = run_sweep_multi(sweep_comm, dist, world, args.sweep_max_bytes)
-                sweep_comm.destroy()
-            elif rank == 0:
-                fused_alone = time_fused_bucket(state.comm, dist, world, args.wire)
-                sweep = run_sweep_loopback(args.sweep_max_bytes)
+                collectives = run_other_collectives(sweep_comm, dist, world)
+            except Exception as e:  # noqa: BLE001
+                optional_errors["allreduce_sweep"] = repr(e)[:300]
+        try:
+            sweep_comm.check()
+        except Exception as e:  # noqa: BLE001
+            optional_errors["sweep_comm"] = repr(e)[:300]
+        sweep_comm.destroy()
+    elif rank == 0 and not args.no_sweep:
+        log("allreduce sweep (loopback)")
+        try:
+            fused_alone = time_fused_bucket(state.comm, dist, world, args.wire)
+            sweep = run_sweep_loopback(args.sweep_max_bytes)
         except Exception as e:  # noqa: BLE001
             optional_errors["allreduce_sweep"] = repr(e)[:300]
 
@@ -536,6 +1007,7 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
+
         def roofline_for(t_us, nelem, where):
             if world > 1:
                 alg = 2 * (world - 1) / world * nelem * wire_b  # NVLink bytes in (== out) per GPU per launch
@@ -549,16 +1021,19 @@ def main():
             alg = nelem * 8  # read fp32 + write fp32
             ach = alg / (t_us * 1e-6) / 1e9
             peak = peaks.get("hbm_gbs", 6650.0)
-            return {"bound": "hbm", "kernel": f"fused gradient scale / wire rounding (world=1), {nelem * 4 >> 20} MiB fp32 bucket, {where}",
-                    "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 3), "traffic": None,
+            return {"bound": "hbm", "kernel": f"k_local_scale<float, bf16_t>: fused gradient scale / wire rounding (world=1), {nelem * 4 >> 20} MiB fp32 bucket, {where}",
+                    "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 3),
+                    "traffic": NCU_TRAFFIC_LOCAL_SCALE_30MIB if nelem == (30 << 18) else None,
+                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture "
+                                    "(profiles/r02_ncu_full_1gpu_details.txt); the written half is still dirty in L2 at kernel end",
                     "launch_us": round(t_us, 2), "algorithmic_bytes": int(alg),
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"}
 
-        # `roofline`: the kernel timed alone (what the burst peak is comparable with);
+        # `roofline`: the kernel timed alone, back to back (what the burst peak is comparable with);
         # `roofline_in_step`: the same kernel inside the training step, where it shares the GPU with the
-        # backward pass on a 32-CTA grid and waits for the slowest rank, so it is an upper bound on time.
+        # backward pass on a small grid and waits for the slowest rank, so it is an upper bound on time.
         roofline_in_step = roofline_for(t_big * 1e3, big // 4, "inside the training step") if t_big else None
-        roofline = roofline_for(fused_alone[0], fused_alone[1], "timed alone") if fused_alone else roofline_in_step
+        roofline = roofline_for(fused_alone[0], fused_alone[1], "timed alone, back-to-back launches") if fused_alone else roofline_in_step
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             cb = int(os.environ.get("BENCH_CPU_BATCH", 16))
@@ -576,8 +1051,9 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(B, world, args.wire),
             "clocks": sampler.summary([win1, win2]) if sampler else None,
-            "e2e": {"value": round(e2e, 1), "unit": "images/s", "h2d_bytes_per_step": x_host_cl.numel() * 4 + y_host.numel() * 8,
-                    "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last_loss},
+            "e2e": {"value": round(e2e, 1), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
+                    "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last_loss,
+                    "input_path": "pinned host -> device on a side stream, double-buffered; loss -> pinned host every step, asynchronous"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "roofline_in_step": roofline_in_step,
@@ -585,8 +1061,12 @@ def main():
             "cpu_baseline": cpu_baseline,
             "baselines": {"nccl_ddp_images_per_sec": round(nccl_ddp, 1) if nccl_ddp else None,
                           "nccl_version": ".".join(map(str, torch.cuda.nccl.version()))},
-            "multicast": bool(state.comm.multicast),
+            "multicast": multicast,
+            "comm_bound": comm_bound,
+            "parity": parity,
+            "p2p": p2p,
             "allreduce_sweep": sweep,
+            "collectives": collectives,
         }
         if optional_errors:
             out["optional_section_errors"] = optional_errors

@@ -175,6 +175,16 @@ uint64_t b200c_comm_seq(const b200c_comm_t* comm);
 void* b200c_comm_symmetric_base(b200c_comm_t* comm);
 uint64_t b200c_comm_symmetric_bytes(const b200c_comm_t* comm);
 
+/* Symmetric pool: allocator entry points in the shape torch.cuda.memory.CUDAPluggableAllocator expects
+ * (alloc(size, device, stream) / free(ptr, size, device, stream)), carving 2 MiB-granular segments out of
+ * the symmetric region of the communicator selected by b200c_pool_bind (one per process; NULL unbinds).
+ * Tensors allocated from a torch.cuda.MemPool built on them are peer-mapped and multicast-bound, so
+ * collectives on them are zero-copy.  First fit over a sorted free list: the same allocation sequence on
+ * every rank yields the same offsets. */
+int b200c_pool_bind(b200c_comm_t* comm);
+void* b200c_pool_malloc(size_t size, int device, void* stream);
+void b200c_pool_free(void* ptr, size_t size, int device, void* stream);
+
 /* ---- collectives (K1-K7, K10-K13 in SURVEY.md §2d) ---- */
 
 /* allReduce(sendptr, recvptr, count, dtype, op, stream): nccl_collective_group.py:181-188,

@@ -442,3 +442,45 @@ def test_full_size_properties_loopback():
         assert all(bool((f == float(W)).all().item()) for f in fs)
     finally:
         w.destroy()
+
+
+def test_symmetric_pool_allocator_mechanics():
+    """torch.cuda.MemPool over a communicator's symmetric region (the zero-copy path itself needs the
+    multicast object, i.e. >= 2 GPUs: tests/test_gpu_multiproc.py): segments come from the region, freed
+    segments are reused first-fit, exhaustion is an ordinary CUDA OOM, and collectives on pool tensors work."""
+    from ant_ray_b200.loopback import LoopbackWorld
+
+    w = LoopbackWorld(2, device=0, key="lb-pool", staging_bytes=4 << 20, symmetric_bytes=64 << 20, timeout_ms=20000)
+    try:
+        c0 = w.comms[0]
+        base = int(c0.lib.b200c_comm_symmetric_base(c0.handle))
+        size = int(c0.lib.b200c_comm_symmetric_bytes(c0.handle))
+        pool = c0.symmetric_pool()
+        with torch.cuda.use_mem_pool(pool):
+            a = torch.full((1 << 20,), 2.0, device="cuda")          # 4 MiB
+            b = torch.full((3 << 20,), 3.0, device="cuda")          # 12 MiB
+        for t in (a, b):
+            assert base <= t.data_ptr() and t.data_ptr() + t.numel() * 4 <= base + size
+        assert a.data_ptr() != b.data_ptr()
+        off_a = a.data_ptr() - base
+        # a plain tensor on the other rank, the pool tensor on this one: the staged path handles the mix
+        other = torch.full((1 << 20,), 5.0, device="cuda")
+        w.run(lambda r, c: c.allreduce((a if r == 0 else other).data_ptr(), (a if r == 0 else other).data_ptr(), 1 << 20, N.FLOAT32, N.SUM))
+        torch.cuda.synchronize()
+        w.check()
+        assert bool((a == 7).all()) and bool((other == 7).all())
+        with pytest.raises(torch.OutOfMemoryError):
+            with torch.cuda.use_mem_pool(pool):
+                torch.empty(size // 4 + 1024, device="cuda")
+        del a
+        torch.cuda.synchronize()
+        # the raw entry points: first fit reuses the lowest free offset
+        p1 = c0.lib.b200c_pool_malloc(1 << 20, 0, None)
+        assert p1 is not None and base <= p1 < base + size
+        c0.lib.b200c_pool_free(p1, 1 << 20, 0, None)
+        p2 = c0.lib.b200c_pool_malloc(1 << 20, 0, None)
+        assert p2 == p1
+        c0.lib.b200c_pool_free(p2, 1 << 20, 0, None)
+        assert off_a % (2 << 20) == 0
+    finally:
+        w.destroy()

@@ -179,7 +179,7 @@ class RawWorker:
         from ant_ray_b200.b200_group import PeerMemoryComm, make_config
 
         self.comm = PeerMemoryComm(self.world, self.rank, "raw", self.rank, None,
-                                   make_config(staging_bytes=8 << 20, symmetric_bytes=16 << 20, timeout_ms=20000), timeout_s=60)
+                                   make_config(staging_bytes=8 << 20, symmetric_bytes=64 << 20, timeout_ms=20000), timeout_s=60)
         return True
 
     def has_multicast(self):
@@ -202,6 +202,29 @@ class RawWorker:
         torch.cuda.synchronize()
         self.comm.check()
         return x.cpu()
+
+    def pool_allreduce(self, n):
+        """Ordinary torch tensors from the communicator's MemPool are zero-copy: NVLS reduces them in place."""
+        from ant_ray_b200 import _native as N
+
+        pool = self.comm.symmetric_pool()
+        with torch.cuda.use_mem_pool(pool):
+            a = torch.empty(n, device="cuda")
+            b = torch.empty(n // 2, device="cuda")
+        base = int(self.comm.lib.b200c_comm_symmetric_base(self.comm.handle))
+        size = int(self.comm.lib.b200c_comm_symmetric_bytes(self.comm.handle))
+        inside = all(base <= t.data_ptr() and t.data_ptr() + t.numel() * 4 <= base + size for t in (a, b))
+        offs = (a.data_ptr() - base, b.data_ptr() - base)
+        a.copy_(make_input(torch.float32, n, self.rank))
+        b.copy_(make_input(torch.float32, n // 2, self.rank + 100))
+        before = N.launch_count()
+        self.comm.allreduce(a.data_ptr(), a.data_ptr(), n, N.FLOAT32, N.SUM, N.ALGO_NVLS)
+        self.comm.allreduce(b.data_ptr(), b.data_ptr(), n // 2, N.FLOAT32, N.SUM, N.ALGO_NVLS)
+        torch.cuda.synchronize()
+        self.comm.check()
+        out = (a.cpu(), b.cpu())
+        del a, b
+        return inside, offs, N.launch_count() - before, out
 
     def broadcast(self, nbytes, root):
         from ant_ray_b200 import _native as N
@@ -297,6 +320,23 @@ def test_nvls_allreduce(raw_world, dtype):
             assert torch.allclose(outs[0].float(), want.float(), rtol=tol, atol=tol * 4), f"nvls {dtype} n={n} sym={symmetric} algo={algo}"
             for r in range(1, W):
                 assert_equal_bits(outs[r], outs[0], "every rank must hold identical bits")
+
+
+def test_symmetric_pool_tensors_are_zero_copy(raw_world):
+    """torch.cuda.MemPool over the symmetric region: same offsets on every rank, NVLS in place, right answer."""
+    actors, W = raw_world
+    if not all(get([a.has_multicast.remote() for a in actors])):
+        pytest.skip("multicast object not bound on this box")
+    n = 1_000_000
+    res = get([a.pool_allreduce.remote(n) for a in actors])
+    assert all(r[0] for r in res), "pool tensors must live inside the symmetric region"
+    assert len({r[1] for r in res}) == 1, "the same allocation sequence must give the same offsets on every rank"
+    assert all(r[2] == 2 for r in res)
+    want_a = O.allreduce([make_input(torch.float32, n, r) for r in range(W)])
+    want_b = O.allreduce([make_input(torch.float32, n // 2, r + 100) for r in range(W)])
+    for r in range(W):
+        assert torch.allclose(res[r][3][0], want_a, rtol=1e-5, atol=4e-5) and torch.allclose(res[r][3][1], want_b, rtol=1e-5, atol=4e-5)
+        assert_equal_bits(res[r][3][0], res[0][3][0], "every rank must hold identical bits")
 
 
 def test_nvls_pipelined_multi_piece_and_fused(raw_world):
