@@ -151,7 +151,7 @@ struct b200c_comm {
   bool bcast_mc = false;   // broadcast through one multicast store stream (wins for W > 2)
   uint32_t pipe_base = 0;  // flag epoch of the round-pipelined kernels (advanced by the round count of each op)
   uint32_t ll_seq = 0;     // LL op counter (flag value of the packed stores; region half = ll_seq & 1)
-  int local_scale_ctas_per_sm = 0;
+  int local_scale_ctas_per_sm = 0, tma_ctas_per_sm = 0;
   uint32_t send_cells[kMaxRanks] = {};
   uint32_t recv_cells[kMaxRanks] = {};
   uint32_t msend_cells = 0;            // multi-reader ring of this rank: cells sent so far
@@ -209,12 +209,12 @@ extern "C" void b200c_default_config(b200c_config_t* cfg) {
   cfg->max_blocks = 296;
   cfg->oneshot_max_bytes = 0;  // 0 = pick by world size in b200c_comm_create
   cfg->nvls_min_bytes = (1ull << 20) + 1;
-  cfg->nvls_pipe_min_bytes = 8ull << 20;  // staged NVLS pieces from 8 MiB up run round-pipelined
+  cfg->nvls_pipe_min_bytes = 32ull << 20;  // staged NVLS pieces from 32 MiB up run round-pipelined (W=8: 540 vs 505 GB/s at 64 MiB)
   cfg->timeout_ms = 600000;  // a slow peer (data loading, first-step autotuning skew) is not a dead peer
   cfg->granule_bytes = 32ull << 10;
-  cfg->ll_max_bytes = 32ull << 10;
+  cfg->ll_max_bytes = 64ull << 10;    // W=8: LL 12 us vs one-shot 13 us at 64 KiB, 15 vs 15 at 128 KiB (profiles/r02_sweep8_small.log)
   cfg->bcast_rounds_min_bytes = 4ull << 20;
-  cfg->nvls_blocks = 0;
+  cfg->nvls_blocks = 32;   // zero-copy NVLS saturates the switch with 32 CTAs; more only scatter the access pattern (r02_sweep8_large.log)
 }
 
 static int ensure_driver() {
@@ -778,19 +778,41 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     if (!has_scale && wire == dtype) { RT(cudaMemcpyAsync(recv, send, count * esz, cudaMemcpyDeviceToDevice, s)); return B200C_OK; }
     CollArgs a; memset(&a, 0, sizeof a);
     a.c = c->dev; a.in = send; a.out = recv; a.n = count; a.has_scale = has_scale; a.scale = scale;
-    int grid = local_scale_grid<float, bf16_t>(c, count * esz);
-    switch (dtype * 16 + wire) {
-      case B200C_FLOAT32 * 16 + B200C_FLOAT32: k_local_scale<float, float><<<grid, kThreads, 0, s>>>(a); break;
-      case B200C_FLOAT32 * 16 + B200C_BFLOAT16: k_local_scale<float, bf16_t><<<grid, kThreads, 0, s>>>(a); break;
-      case B200C_FLOAT32 * 16 + B200C_FLOAT16: k_local_scale<float, f16_t><<<grid, kThreads, 0, s>>>(a); break;
-      case B200C_BFLOAT16 * 16 + B200C_BFLOAT16: k_local_scale<bf16_t, bf16_t><<<grid, kThreads, 0, s>>>(a); break;
-      case B200C_FLOAT16 * 16 + B200C_FLOAT16: k_local_scale<f16_t, f16_t><<<grid, kThreads, 0, s>>>(a); break;
-      case B200C_FLOAT64 * 16 + B200C_FLOAT64: k_local_scale<double, double><<<grid, kThreads, 0, s>>>(a); break;
-      default:
-        // integer AVG over one rank is the identity
-        if (send != recv) RT(cudaMemcpyAsync(recv, send, count * esz, cudaMemcpyDeviceToDevice, s));
-        return B200C_OK;
+    // Large, 16-byte aligned buffers stream through shared memory with the bulk copy engine (TMA); the
+    // plain LSU kernel takes small buffers, unaligned views and the sub-tile tail.
+    static const bool use_tma = [] { const char* e = getenv("B200COLL_LOCAL_SCALE_TMA"); return !e || e[0] != '0'; }();
+    size_t tma_elems = 0;
+    if (use_tma && count * esz >= (1u << 20) && ((uintptr_t)send & 15) == 0 && ((uintptr_t)recv & 15) == 0 &&
+        (dtype == B200C_FLOAT32 || dtype == B200C_BFLOAT16 || dtype == B200C_FLOAT16)) {
+      size_t ntiles = count * esz / kTmaTileBytes;
+      tma_elems = ntiles * kTmaTileBytes / esz;
+      if (c->tma_ctas_per_sm == 0) {
+        int nb = 0;
+        cudaFuncSetAttribute(k_local_scale_tma<float, bf16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+        cudaFuncSetAttribute(k_local_scale_tma<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+        cudaFuncSetAttribute(k_local_scale_tma<float, f16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+        cudaFuncSetAttribute(k_local_scale_tma<bf16_t, bf16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+        cudaFuncSetAttribute(k_local_scale_tma<f16_t, f16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_local_scale_tma<float, bf16_t>, kTmaThreads, kTmaSmemBytes) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
+        c->tma_ctas_per_sm = nb;
+      }
+      size_t cap = (size_t)c->sm_count * c->tma_ctas_per_sm;
+      int tgrid = (int)(ntiles < cap ? ntiles : cap);
+      switch (dtype * 16 + wire) {
+        case B200C_FLOAT32 * 16 + B200C_FLOAT32: k_local_scale_tma<float, float><<<tgrid, kTmaThreads, kTmaSmemBytes, s>>>(a); break;
+        case B200C_FLOAT32 * 16 + B200C_BFLOAT16: k_local_scale_tma<float, bf16_t><<<tgrid, kTmaThreads, kTmaSmemBytes, s>>>(a); break;
+        case B200C_FLOAT32 * 16 + B200C_FLOAT16: k_local_scale_tma<float, f16_t><<<tgrid, kTmaThreads, kTmaSmemBytes, s>>>(a); break;
+        case B200C_BFLOAT16 * 16 + B200C_BFLOAT16: k_local_scale_tma<bf16_t, bf16_t><<<tgrid, kTmaThreads, kTmaSmemBytes, s>>>(a); break;
+        default: k_local_scale_tma<f16_t, f16_t><<<tgrid, kTmaThreads, kTmaSmemBytes, s>>>(a); break;
+      }
+      rc = launch_check(c, "local_scale_tma");
+      if (rc) return rc;
+      if (tma_elems == count) return B200C_OK;
+      a.in = static_cast<const char*>(send) + tma_elems * esz;
+      a.out = static_cast<char*>(recv) + tma_elems * esz;
+      a.n = count - tma_elems;
     }
+    int grid = local_scale_grid<float, bf16_t>(c, a.n * esz);
     return launch_check(c, "local_scale");
   }
 
@@ -799,9 +821,16 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
   if ((algo == B200C_ALGO_NVLS || algo == B200C_ALGO_NVLS_PIPE) && !nvls_ok) return fail(B200C_EUNSUPPORTED, "NVLS needs a bound multicast object, SUM/AVG and f32/bf16/f16");
   const bool ll_ok = wire == dtype && c->ll_words && count * esz <= c->ll_words * 4;
   if (algo == B200C_ALGO_LL && !ll_ok) return fail(B200C_EUNSUPPORTED, "LL needs wire == dtype and at most %zu bytes (ll_max_bytes)", c->ll_words * 4);
-  const uint32_t nvls_cap = c->cfg.nvls_blocks ? c->cfg.nvls_blocks : c->cfg.max_blocks;
+  // the zero-copy kernel is pure switch traffic (few CTAs are best); the staged kernels also do the local copies
+  const uint32_t nvls_sym_cap = c->cfg.nvls_blocks && c->cfg.nvls_blocks < c->cfg.max_blocks ? c->cfg.nvls_blocks : c->cfg.max_blocks;
   const char* in = static_cast<const char*>(send);
   char* out = static_cast<char*>(recv);
+  // in place, same dtype on the wire, inside the symmetric region: eligible for the zero-copy path
+  bool in_sym = false;
+  if (wire == dtype && send == recv && c->sym_bytes && (((uintptr_t)send) & 15) == 0 && (count * esz) % 16 == 0) {
+    const char* base = c->arena[c->rank] + c->off_sym;
+    in_sym = in >= base && in + count * esz <= base + c->sym_bytes;
+  }
   size_t done = 0;
   while (done < count) {
     size_t left = count - done;
@@ -812,7 +841,7 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     if (al == B200C_ALGO_AUTO) {
       if (ll_ok && count * esz <= c->cfg.ll_max_bytes) al = B200C_ALGO_LL;
       else if (bytes_left <= c->cfg.oneshot_max_bytes) al = B200C_ALGO_ONESHOT;
-      else if (nvls_ok && W > 2 && bytes_left >= c->cfg.nvls_min_bytes) al = B200C_ALGO_NVLS;
+      else if (nvls_ok && W > 2 && bytes_left >= c->cfg.nvls_min_bytes && (W >= 6 || in_sym)) al = B200C_ALGO_NVLS;  // W = 4: two-shot beats STAGED NVLS (r02_sweep4_large.log)
       else al = B200C_ALGO_TWOSHOT;
     }
     CollArgs a;
@@ -823,11 +852,7 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     int grid;
     uint32_t rounds = 0;
     // symmetric zero-copy NVLS: buffer lives in the symmetric region at the same offset everywhere
-    bool sym = false;
-    if (al == B200C_ALGO_NVLS && wire == dtype && send == recv && c->sym_bytes) {
-      char* base = c->arena[c->rank] + c->off_sym;
-      if (in >= base && in + count * esz <= base + c->sym_bytes && (((uintptr_t)a.in) & 15) == 0 && (left * esz) % 16 == 0) sym = true;
-    }
+    const bool sym = al == B200C_ALGO_NVLS && in_sym;
     if (al == B200C_ALGO_LL) {
       n = left;
       a.chunk = round_up(n, vec);
@@ -857,10 +882,10 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
       if (!sym && algo == B200C_ALGO_AUTO && c->cfg.nvls_pipe_min_bytes && n * wsz >= c->cfg.nvls_pipe_min_bytes) pipe = true;
       if (sym) pipe = false;  // nothing to overlap: the symmetric path has no staging copies
       if (pipe) {
-        plan_rounds(a.chunk, wsz, vec, nvls_cap, c->cfg.granule_bytes, &a.tile, &grid, &rounds);
+        plan_rounds(a.chunk, wsz, vec, c->cfg.max_blocks, c->cfg.granule_bytes, &a.tile, &grid, &rounds);
         a.pipe_base = c->pipe_base;
       } else {
-        plan_tiles(a.chunk, wsz, vec, nvls_cap, kMinTileBytes, c->cfg.granule_bytes, &a.tile, &grid);
+        plan_tiles(a.chunk, wsz, vec, sym ? nvls_sym_cap : c->cfg.max_blocks, kMinTileBytes, c->cfg.granule_bytes, &a.tile, &grid);
       }
     }
     a.n = n;

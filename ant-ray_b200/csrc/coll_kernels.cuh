@@ -532,4 +532,98 @@ __global__ void __launch_bounds__(kThreads) k_local_scale(const __grid_constant_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// TMA-staged variant of k_local_scale: the streaming is done by the copy engine, not by LSU
+// instructions.  One elected thread issues bulk asynchronous copies (cp.async.bulk, SASS UBLKCP)
+// global -> shared, completion is signalled on an mbarrier (complete_tx::bytes); the CTA converts the
+// tile in shared memory; the same thread sends it back with a bulk shared -> global copy
+// (bulk_group).  kTmaStages tiles are in flight per CTA, so the loads of tiles i+1..i+3 and the store
+// of tile i-1 overlap the arithmetic on tile i without costing registers (the LSU version keeps four
+// 16-byte vectors per thread in registers and gets 2 CTAs/SM; this one keeps none).
+// Requires 16-byte aligned in/out; handles n / tile whole tiles, the caller's plain kernel the rest.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTmaThreads = 256;
+constexpr int kTmaStages = 4;
+constexpr int kTmaTileBytes = 16384;
+constexpr int kTmaSmemBytes = kTmaStages * kTmaTileBytes + kTmaStages * 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+
+template <typename TI, typename TW>
+__global__ void __launch_bounds__(kTmaThreads) k_local_scale_tma(const __grid_constant__ CollArgs a) {
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tma_smem + kTmaStages * kTmaTileBytes);
+  constexpr int VI = 16 / sizeof(TI);
+  const char* in = static_cast<const char*>(a.in);
+  char* out = static_cast<char*>(a.out);
+  const size_t ntiles = a.n * sizeof(TI) / kTmaTileBytes;
+  const int tid = threadIdx.x;
+  const size_t mine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (tid == 0) {
+    for (int s = 0; s < kTmaStages; s++) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < kTmaStages && (size_t)s < mine; s++) {
+      mbar_expect_tx(&bars[s], kTmaTileBytes);
+      bulk_g2s(tma_smem + s * kTmaTileBytes, in + (blockIdx.x + (size_t)s * gridDim.x) * kTmaTileBytes, kTmaTileBytes, &bars[s]);
+    }
+  }
+  for (size_t i = 0; i < mine; i++) {
+    const int stage = (int)(i % kTmaStages);
+    mbar_wait(&bars[stage], (uint32_t)((i / kTmaStages) & 1));
+    uint4* tile = reinterpret_cast<uint4*>(tma_smem + stage * kTmaTileBytes);
+#pragma unroll
+    for (int j = 0; j < kTmaTileBytes / 16 / kTmaThreads; j++) {
+      Pack16<TI> p;
+      p.u = tile[tid + j * kTmaThreads];
+#pragma unroll
+      for (int e = 0; e < VI; e++) p.e[e] = local_scale_one<TI, TW>(p.e[e], a);
+      tile[tid + j * kTmaThreads] = p.u;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the copy engine
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(out + (blockIdx.x + i * gridDim.x) * kTmaTileBytes, tile, kTmaTileBytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      // the stage converted one iteration ago is free once ITS store has finished reading shared memory
+      // (at most the store just issued may still be pending): refill it with the tile kTmaStages ahead
+      if (i >= 1 && i - 1 + kTmaStages < mine) {
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        const int ps = (int)((i - 1) % kTmaStages);
+        mbar_expect_tx(&bars[ps], kTmaTileBytes);
+        bulk_g2s(tma_smem + ps * kTmaTileBytes, in + (blockIdx.x + (i - 1 + kTmaStages) * gridDim.x) * kTmaTileBytes, kTmaTileBytes, &bars[ps]);
+      }
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores must have landed before the CTA retires
+}
+
 }  // namespace b200c

@@ -60,7 +60,7 @@ def test_allreduce_ops(world, dtype, opname, algo):
         _run_allreduce(world, dtype, n, opname, algo)
 
 
-LL_SIZES = [1, 3, 10, 257, 4000]   # 4000 x 8-byte elements = 32,000 bytes: just under the 32 KiB LL capacity
+LL_SIZES = [1, 3, 10, 257, 4000, 8190]   # 8190 x 8-byte elements = 65,520 bytes: just under the 64 KiB LL capacity
 
 
 @pytest.mark.parametrize("dtype", INT_DTYPES + FLOAT_DTYPES)
@@ -80,11 +80,12 @@ def test_allreduce_ll_ops(world, dtype, opname):
 
 def test_allreduce_ll_limits_and_auto(world):
     """AUTO picks LL up to ll_max_bytes; asking for LL beyond the region's capacity is refused, not truncated."""
-    _run_allreduce(world, torch.float32, 8192, "sum", N.ALGO_AUTO)       # exactly 32 KiB -> LL
-    _run_allreduce(world, torch.float32, 8193, "sum", N.ALGO_AUTO)       # one element more -> one-shot
-    x = torch.ones(8193, device="cuda")
+    cap = int(world.comms[0].config.ll_max_bytes) // 4                    # fp32 elements the LL region holds (64 KiB)
+    _run_allreduce(world, torch.float32, cap, "sum", N.ALGO_AUTO)        # exactly ll_max_bytes -> LL
+    _run_allreduce(world, torch.float32, cap + 1, "sum", N.ALGO_AUTO)    # one element more -> one-shot
+    x = torch.ones(cap + 1, device="cuda")
     with pytest.raises(N.B200CollError) as ei:
-        world.comms[0].allreduce(x.data_ptr(), x.data_ptr(), 8193, N.FLOAT32, N.SUM, N.ALGO_LL)
+        world.comms[0].allreduce(x.data_ptr(), x.data_ptr(), cap + 1, N.FLOAT32, N.SUM, N.ALGO_LL)
     assert ei.value.status == N.EUNSUPPORTED
     # the refused call must not have consumed a sequence number: the next op still lines up with the peers
     _run_allreduce(world, torch.int32, 100, "sum", N.ALGO_LL)
