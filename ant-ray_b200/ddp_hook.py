@@ -36,7 +36,9 @@ class B200GradState:
         self.comm = comm
         self.wire = _WIRE[wire]
         self.algo = algo
-        self.stream = torch.cuda.Stream(device=comm.device)
+        # high priority: the few CTAs of a bucket reduction take SM slots as soon as the backward kernels free any,
+        # instead of queueing behind their whole grids (every rank's matching block must be resident to progress)
+        self.stream = torch.cuda.Stream(device=comm.device, priority=-1)
         self.launches = 0
         self.bytes = 0
         self.time_kernels = time_kernels
