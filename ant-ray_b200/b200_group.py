@@ -131,6 +131,9 @@ def make_config(**overrides):
         "B200COLL_LL_MAX_BYTES": ("ll_max_bytes", int),
         "B200COLL_BCAST_ROUNDS_MIN_BYTES": ("bcast_rounds_min_bytes", int),
         "B200COLL_NVLS_BLOCKS": ("nvls_blocks", int),
+        "B200COLL_NVLS_LANES": ("nvls_lanes", int),
+        "B200COLL_LANE_GRANULE_BYTES": ("lane_granule_bytes", int),
+        "B200COLL_NVLS_LANES_MIN_BYTES": ("nvls_lanes_min_bytes", int),
         "B200COLL_TIMEOUT_MS": ("timeout_ms", int),
         "B200COLL_P2P_SLOT_BYTES": ("p2p_slot_bytes", int),
         "B200COLL_P2P_SLOTS": ("p2p_slots", int),

@@ -214,6 +214,9 @@ extern "C" void b200c_default_config(b200c_config_t* cfg) {
   cfg->granule_bytes = 32ull << 10;
   cfg->ll_max_bytes = 64ull << 10;    // W=8: LL 12 us vs one-shot 13 us at 64 KiB, 15 vs 15 at 128 KiB (profiles/r02_sweep8_small.log)
   cfg->bcast_rounds_min_bytes = 4ull << 20;
+  cfg->nvls_lanes = 48;
+  cfg->lane_granule_bytes = 64ull << 10;
+  cfg->nvls_lanes_min_bytes = 0;   // opt-in until measured on the target box
   cfg->nvls_blocks = 32;   // zero-copy NVLS saturates the switch with 32 CTAs; more only scatter the access pattern (r02_sweep8_large.log)
 }
 
@@ -296,6 +299,10 @@ extern "C" int b200c_comm_create(int rank, int world, int device, const b200c_co
   if (cfg.granule_bytes % 16384) return fail(B200C_EINVAL, "granule_bytes must be a multiple of 16 KiB");
   if (cfg.ll_max_bytes > (1ull << 20)) return fail(B200C_EINVAL, "ll_max_bytes must be <= 1 MiB");
   if (cfg.nvls_blocks > (uint32_t)kMaxBlocks) return fail(B200C_EINVAL, "nvls_blocks %u > %d", cfg.nvls_blocks, kMaxBlocks);
+  if (cfg.nvls_lanes == 0) cfg.nvls_lanes = 48;
+  if (cfg.nvls_lanes > cfg.max_blocks / 2) cfg.nvls_lanes = cfg.max_blocks / 2 ? cfg.max_blocks / 2 : 1;
+  if (cfg.lane_granule_bytes == 0) cfg.lane_granule_bytes = 64ull << 10;
+  if (cfg.lane_granule_bytes % 8192) return fail(B200C_EINVAL, "lane_granule_bytes must be a multiple of 8 KiB");
   // measured crossovers (profiles/r01_sweep_*): W=2 one-shot wins to 8 MiB; W=8 one-shot 23 us vs NVLS 28 us at 1 MiB
   if (cfg.oneshot_max_bytes == 0) cfg.oneshot_max_bytes = world <= 2 ? (8ull << 20) : (1ull << 20);
 
@@ -738,8 +745,9 @@ static void launch_mixed(int algo, const CollArgs& a, int grid, cudaStream_t s) 
   else k_allreduce_twoshot<TI, TW, B200C_SUM><<<grid, kThreads, 0, s>>>(a);
 }
 template <typename TI, typename TW>
-static void launch_nvls(const CollArgs& a, int grid, cudaStream_t s, bool pipe) {
-  if (pipe) k_allreduce_nvls_rounds<TI, TW><<<grid, kThreads, 0, s>>>(a);
+static void launch_nvls(const CollArgs& a, int grid, cudaStream_t s, bool pipe, bool lanes = false) {
+  if (lanes) k_allreduce_nvls_lanes<TI, TW><<<grid, kThreads, 0, s>>>(a);
+  else if (pipe) k_allreduce_nvls_rounds<TI, TW><<<grid, kThreads, 0, s>>>(a);
   else k_allreduce_nvls<TI, TW><<<grid, kThreads, 0, s>>>(a);
 }
 template <typename TI, typename TW>
@@ -767,7 +775,7 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     if (!(dtype == B200C_FLOAT32 && (wire == B200C_BFLOAT16 || wire == B200C_FLOAT16))) return fail(B200C_EUNSUPPORTED, "wire dtype %d for buffer dtype %d", wire, dtype);
     if (op != B200C_SUM && op != B200C_AVG) return fail(B200C_EUNSUPPORTED, "compressed wire supports SUM/AVG only");
   }
-  if (algo < B200C_ALGO_AUTO || algo > B200C_ALGO_LL) return fail(B200C_EINVAL, "bad algo %d", algo);
+  if (algo < B200C_ALGO_AUTO || algo > B200C_ALGO_NVLS_LANES) return fail(B200C_EINVAL, "bad algo %d", algo);
   if (op == B200C_AVG) { has_scale = 1; scale = 1.f / (float)c->world; }
   if (count == 0) return B200C_OK;
   DeviceGuard g(c->device);
@@ -818,7 +826,7 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
 
   const bool nvls_ok = c->mc_arena && (op == B200C_SUM || op == B200C_AVG) &&
                        (wire == B200C_FLOAT32 || wire == B200C_BFLOAT16 || wire == B200C_FLOAT16);
-  if ((algo == B200C_ALGO_NVLS || algo == B200C_ALGO_NVLS_PIPE) && !nvls_ok) return fail(B200C_EUNSUPPORTED, "NVLS needs a bound multicast object, SUM/AVG and f32/bf16/f16");
+  if ((algo == B200C_ALGO_NVLS || algo == B200C_ALGO_NVLS_PIPE || algo == B200C_ALGO_NVLS_LANES) && !nvls_ok) return fail(B200C_EUNSUPPORTED, "NVLS needs a bound multicast object, SUM/AVG and f32/bf16/f16");
   const bool ll_ok = wire == dtype && c->ll_words && count * esz <= c->ll_words * 4;
   if (algo == B200C_ALGO_LL && !ll_ok) return fail(B200C_EUNSUPPORTED, "LL needs wire == dtype and at most %zu bytes (ll_max_bytes)", c->ll_words * 4);
   // the zero-copy kernel is pure switch traffic (few CTAs are best); the staged kernels also do the local copies
@@ -836,8 +844,9 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     size_t left = count - done;
     size_t bytes_left = left * wsz;
     int al = algo;
-    bool pipe = false;
+    bool pipe = false, lanes = false;
     if (al == B200C_ALGO_NVLS_PIPE) { al = B200C_ALGO_NVLS; pipe = true; }
+    if (al == B200C_ALGO_NVLS_LANES) { al = B200C_ALGO_NVLS; lanes = true; }
     if (al == B200C_ALGO_AUTO) {
       if (ll_ok && count * esz <= c->cfg.ll_max_bytes) al = B200C_ALGO_LL;
       else if (bytes_left <= c->cfg.oneshot_max_bytes) al = B200C_ALGO_ONESHOT;
@@ -879,9 +888,33 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
       a.chunk = round_up((n + W - 1) / W, vec);
       a.symmetric = sym ? 1 : 0;
       a.sym_off = sym ? (size_t)((const char*)a.in - c->arena[c->rank]) : 0;
-      if (!sym && algo == B200C_ALGO_AUTO && c->cfg.nvls_pipe_min_bytes && n * wsz >= c->cfg.nvls_pipe_min_bytes) pipe = true;
-      if (sym) pipe = false;  // nothing to overlap: the symmetric path has no staging copies
-      if (pipe) {
+      if (!sym && algo == B200C_ALGO_AUTO && c->cfg.nvls_lanes_min_bytes && left * wsz >= c->cfg.nvls_lanes_min_bytes) lanes = true;
+      if (!sym && !lanes && algo == B200C_ALGO_AUTO && c->cfg.nvls_pipe_min_bytes && n * wsz >= c->cfg.nvls_pipe_min_bytes) pipe = true;
+      if (sym) pipe = lanes = false;  // nothing to overlap: the symmetric path has no staging copies
+      if (lanes) {
+        // the ring is rewritten every three rounds, so the staging capacity does not bound the piece: take it all
+        n = left;
+        a.chunk = round_up((n + W - 1) / W, vec);
+        uint32_t L = c->cfg.nvls_lanes;
+        uint32_t Kc = c->cfg.max_blocks / L - 1;
+        if (Kc > 7) Kc = 7;
+        if (Kc < 1) Kc = 1;
+        // granule: the configured size, smaller for messages that would otherwise give a lane fewer than ~4 rounds
+        size_t tb = c->cfg.lane_granule_bytes, chunk_bytes = a.chunk * wsz;
+        size_t want = chunk_bytes / ((size_t)L * 4) / 8192 * 8192;
+        if (want < 8192) want = 8192;
+        if (tb > want) tb = want;
+        size_t ring = (size_t)L * kLaneSlots * W * tb;
+        while (ring > c->cfg.staging_bytes && tb > 8192) { tb -= 8192; ring = (size_t)L * kLaneSlots * W * tb; }
+        if (ring > c->cfg.staging_bytes) return fail(B200C_EINVAL, "staging_bytes too small for the lane kernel's ring (%zu bytes)", ring);
+        a.tile = tb / wsz;
+        a.lane_copy = (int)Kc;
+        size_t ngran = (a.chunk + a.tile - 1) / a.tile;
+        uint32_t used = (uint32_t)(ngran < L ? ngran : L);   // lanes that own at least one granule
+        grid = (int)(used * (1 + Kc));
+        rounds = (uint32_t)((ngran + used - 1) / used);
+        a.pipe_base = c->pipe_base;
+      } else if (pipe) {
         plan_rounds(a.chunk, wsz, vec, c->cfg.max_blocks, c->cfg.granule_bytes, &a.tile, &grid, &rounds);
         a.pipe_base = c->pipe_base;
       } else {
@@ -890,13 +923,13 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     }
     a.n = n;
     // a symmetric buffer must sit at the same arena offset on every rank: the offset is part of the signature
-    a.sig = make_sig(OPC_ALLREDUCE, dtype * 16 + wire, op, n, sym ? (int)((a.sym_off >> 4) & 0x3fffffff) : -1, al * 4 + (sym ? 1 : 0) + (pipe ? 2 : 0));
+    a.sig = make_sig(OPC_ALLREDUCE, dtype * 16 + wire, op, n, sym ? (int)((a.sym_off >> 4) & 0x3fffffff) : -1, al * 8 + (sym ? 1 : 0) + (pipe ? 2 : 0) + (lanes ? 4 : 0));
     if (al == B200C_ALGO_NVLS) {
-      if (dtype == B200C_FLOAT32 && wire == B200C_FLOAT32) launch_nvls<float, float>(a, grid, s, pipe);
-      else if (dtype == B200C_BFLOAT16) launch_nvls<bf16_t, bf16_t>(a, grid, s, pipe);
-      else if (dtype == B200C_FLOAT16) launch_nvls<f16_t, f16_t>(a, grid, s, pipe);
-      else if (wire == B200C_BFLOAT16) launch_nvls<float, bf16_t>(a, grid, s, pipe);
-      else launch_nvls<float, f16_t>(a, grid, s, pipe);
+      if (dtype == B200C_FLOAT32 && wire == B200C_FLOAT32) launch_nvls<float, float>(a, grid, s, pipe, lanes);
+      else if (dtype == B200C_BFLOAT16) launch_nvls<bf16_t, bf16_t>(a, grid, s, pipe, lanes);
+      else if (dtype == B200C_FLOAT16) launch_nvls<f16_t, f16_t>(a, grid, s, pipe, lanes);
+      else if (wire == B200C_BFLOAT16) launch_nvls<float, bf16_t>(a, grid, s, pipe, lanes);
+      else launch_nvls<float, f16_t>(a, grid, s, pipe, lanes);
     } else if (wire != dtype) {
       if (wire == B200C_BFLOAT16) launch_mixed<float, bf16_t>(al, a, grid, s);
       else launch_mixed<float, f16_t>(al, a, grid, s);

@@ -484,6 +484,112 @@ __global__ void __launch_bounds__(kThreads, 2) k_allreduce_nvls_rounds(const __g
   nvls_stage_out<TI, TW>(a, mine, out, lo_of(R - 1), hi_of(R - 1));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Lane-structured staged NVLS allreduce (the largest plain tensors).  The grid is cut into L lanes of
+// 1 + Kc CTAs.  CTA 0 of a lane only talks to the switch (multimem.ld_reduce / multimem.st and the two
+// cross-GPU flags of its lane); the other Kc CTAs only move data locally (user tensor -> ring, ring ->
+// user tensor).  Roles meet through flags in LOCAL memory, so
+//   * the system-scope release fences (3 us on a quiet SM, 15-20 us on an SM that streams stores:
+//     profiles/r02_probe*_exp.log E3) sit in the switch CTAs, where nothing else streams, and never stall
+//     a copy;
+//   * few CTAs issue multimem traffic (the switch saturates with ~32 CTAs; more only scatter the access
+//     pattern) while many CTAs drive the local HBM copies;
+//   * staging is a small ring — lane l, slot q % 3, chunk j, T elements — that is rewritten every three
+//     rounds and therefore stays in L2: the switch reads it from L2, the results land in L2, the copy-out
+//     reads L2; HBM only sees the user tensor once in and once out.  (It also removes the staging-capacity
+//     limit: one launch handles a message of any size.)
+// Lane l owns granules l, l + L, l + 2L, ... (T elements) of every rank chunk; round q of lane l is granule
+// q*L + l.  Order inside a copy CTA: in(q), out(q-2) — three ring slots make in(q) safe: slot q%3 was read out
+// in out(q-3), one iteration earlier, and every peer finished reducing it before that (flagB).
+// Flags: laneIn[lane][k] (local, copy CTA k -> switch CTA), pipeA[lane][src] ("src staged round q"),
+// pipeB[lane][src] ("src reduced + broadcast its chunk of round q", also raised on the own arena).
+// ---------------------------------------------------------------------------------------------
+constexpr int kLaneSlots = 3;
+
+template <typename TI, typename TW>
+__global__ void __launch_bounds__(kThreads, 2) k_allreduce_nvls_lanes(const __grid_constant__ CollArgs a) {
+  const DevComm& c = a.c;
+  const int r = c.rank, W = c.world, t = threadIdx.x;
+  if (!coll_prologue(a)) return;
+  check_signature(a);
+  constexpr int V = 16 / sizeof(TW);
+  const int per = 1 + a.lane_copy, Kc = a.lane_copy;
+  const int lane = blockIdx.x / per, role = blockIdx.x % per, L = gridDim.x / per;
+  const size_t T = a.tile;
+  const size_t ngran = (a.chunk + T - 1) / T;
+  const int R = (size_t)lane < ngran ? (int)((ngran - lane + L - 1) / L) : 0;
+  const size_t half_off = c.off_staging + (size_t)(a.seq & 1) * c.staging_bytes;
+  auto ring_elem = [&](int slot, int j) { return (((size_t)lane * kLaneSlots + slot) * W + j) * T; };
+  uint32_t* laneIn = reinterpret_cast<uint32_t*>(c.arena[r] + kOffLaneIn) + (size_t)lane * 8;
+  if (role == 0) {
+    // ------------------------------------------------------------------ switch CTA
+    const uint32_t* fA = reinterpret_cast<const uint32_t*>(c.arena[r] + kOffPipeA) + (size_t)lane * 8;
+    for (int q = 0; q < R; q++) {
+      const uint32_t v = a.pipe_base + q + 1;
+      int ok = 1;
+      if (t < Kc) ok = wait_flag(laneIn + t, v, c, r, 1);
+      if (!__syncthreads_and(ok)) return;
+      if (t < W && t != r) st_release_sys(reinterpret_cast<uint32_t*>(c.arena[t] + kOffPipeA) + (size_t)lane * 8 + r, v);
+      ok = 1;
+      if (t < W && t != r) ok = wait_flag(fA + t, v, c, t, 1);
+      if (!__syncthreads_and(ok)) return;
+      const size_t g0 = ((size_t)q * L + lane) * T;
+      const size_t lo = (size_t)r * a.chunk + g0;
+      const size_t hi = (size_t)r * a.chunk + (g0 + T < a.chunk ? g0 + T : a.chunk);
+      const size_t cnt = clip_count(lo, hi, a.n);
+      if (cnt) nvls_reduce_bcast<TW>(c.mc_arena + half_off + ring_elem(q % kLaneSlots, r) * sizeof(TW), (cnt + V - 1) / V, a);
+      __syncthreads();
+      if (t < W) st_release_sys(reinterpret_cast<uint32_t*>(c.arena[t] + kOffPipeB) + (size_t)lane * 8 + r, v);
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- copy CTA
+  const int k = role - 1;
+  const TI* in = static_cast<const TI*>(a.in);
+  TI* out = static_cast<TI*>(a.out);
+  TW* ring = reinterpret_cast<TW*>(c.arena[r] + half_off);
+  const size_t Tk = ((T + Kc - 1) / Kc + V - 1) / V * V;   // this CTA's share of a granule (whole vectors)
+  const uint32_t* fB = reinterpret_cast<const uint32_t*>(c.arena[r] + kOffPipeB) + (size_t)lane * 8;
+  for (int q = 0; q < R + 2; q++) {
+    if (q < R) {
+      const size_t g0 = ((size_t)q * L + lane) * T;
+      const size_t s0 = (size_t)k * Tk, s1 = s0 + Tk < T ? s0 + Tk : T;
+      for (int j = 0; j < W && s0 < s1; j++) {
+        const size_t base = (size_t)j * a.chunk;
+        const size_t cend = base + a.chunk;   // the granule may reach past the chunk on its last round
+        size_t lo = base + g0 + s0, hi = base + g0 + s1;
+        if (hi > cend) hi = cend;
+        size_t cnt = lo < hi ? clip_count(lo, hi, a.n) : 0;
+        TW* dst = ring + ring_elem(q % kLaneSlots, j) + s0;
+        if (cnt) move_tile<TI, TW, false>(dst, in + lo, cnt);
+        size_t padded = (cnt + V - 1) / V * V;
+        if (cnt && padded > cnt && padded <= s1 - s0) {   // zero-pad the message's last vector for the switch
+          TW z = Traits<TW>::from_acc((typename Traits<TW>::A)0);
+          for (size_t e = cnt + t; e < padded; e += kThreads) dst[e] = z;
+        }
+      }
+      __syncthreads();
+      if (t == 0) st_release_sys(laneIn + k, a.pipe_base + q + 1);
+    }
+    if (q >= 2) {
+      const int qq = q - 2;
+      int ok = 1;
+      if (t < W) ok = wait_flag(fB + t, a.pipe_base + qq + 1, c, t, 2);
+      if (!__syncthreads_and(ok)) return;
+      const size_t g0 = ((size_t)qq * L + lane) * T;
+      const size_t s0 = (size_t)k * Tk, s1 = s0 + Tk < T ? s0 + Tk : T;
+      for (int j = 0; j < W && s0 < s1; j++) {
+        const size_t base = (size_t)j * a.chunk;
+        const size_t cend = base + a.chunk;
+        size_t lo = base + g0 + s0, hi = base + g0 + s1;
+        if (hi > cend) hi = cend;
+        size_t cnt = lo < hi ? clip_count(lo, hi, a.n) : 0;
+        if (cnt) move_tile<TW, TI, true>(out + lo, ring + ring_elem(qq % kLaneSlots, j) + s0, cnt);
+      }
+    }
+  }
+}
+
 // world == 1: no peers, only the wire rounding and the scale remain (the DDP hook at N = 1).
 // Grid-stride over 16-byte vectors, four loads in flight per thread; the host sizes the grid to the
 // resident capacity (no second, partial wave); HBM-bound (read n, write n).

@@ -37,7 +37,8 @@ constexpr int kMaxCells = 1024;
 constexpr size_t kOffP2PAck = kOffP2PReady + 8 * kMaxCells * 4;  // u32 [8 dst][kMaxCells]
 constexpr size_t kOffMReady = kOffP2PAck + 8 * kMaxCells * 4;  // u32 [8 src][kMaxCells]  multi-reader ring: cell ready (on each reader)
 constexpr size_t kOffMAck = kOffMReady + 8 * kMaxCells * 4;    // u32 [8 dst][kMaxCells]  multi-reader ring: cell consumed (on the source)
-constexpr size_t kPadUsed = kOffMAck + 8 * kMaxCells * 4;
+constexpr size_t kOffLaneIn = kOffMAck + 8 * kMaxCells * 4;     // u32 [kMaxBlocks lanes][8 copy CTAs]  lane kernel: "my share of round q is staged" (local)
+constexpr size_t kPadUsed = kOffLaneIn + kMaxBlocks * 8 * 4;
 static_assert(kPadUsed <= kPadBytes, "signal pad overflow");
 
 // host-pinned, device-mapped status block
@@ -84,6 +85,7 @@ struct CollArgs {
   float scale;
   uint32_t pipe_base;  // round-pipelined kernels: flag value of round q is pipe_base + q + 1
   uint32_t ll_seq;     // LL kernels: per-communicator LL op counter (flag value; half = ll_seq & 1)
+  int lane_copy;       // lane kernel: copy CTAs per lane (each lane = 1 switch CTA + lane_copy copy CTAs)
   int symmetric;   // NVLS: in/out already live at the same offset of the symmetric region
   size_t sym_off;  // arena offset of that buffer
   const void* in_ptrs[kMaxRanks];

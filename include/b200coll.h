@@ -63,7 +63,8 @@ typedef enum {
   B200C_ALGO_TWOSHOT = 2, /* push reduce-scatter + pull all-gather over peer memory */
   B200C_ALGO_NVLS = 3,    /* multimem.ld_reduce / multimem.st on the NVSwitch multicast object */
   B200C_ALGO_NVLS_PIPE = 4,/* same, staged copies overlapped with the switch traffic (per-round flags, software-pipelined blocks) */
-  B200C_ALGO_LL = 5        /* packed {data, flag} 8-byte stores, one NVLink hop, no fence: small messages */
+  B200C_ALGO_LL = 5,       /* packed {data, flag} 8-byte stores, one NVLink hop, no fence: small messages */
+  B200C_ALGO_NVLS_LANES = 6 /* staged NVLS in lanes: few switch-only CTAs + many copy-only CTAs over an L2-resident staging ring */
 } b200c_algo_t;
 
 typedef enum {
@@ -99,8 +100,10 @@ typedef struct {
   uint64_t granule_bytes;      /* block-cyclic granule of the large-message kernels (multiple of 16 KiB; 0 = 32 KiB) */
   uint64_t ll_max_bytes;       /* AUTO: same-type allreduce <= this goes by the LL kernel; also sizes the LL region (0 = no LL) */
   uint64_t bcast_rounds_min_bytes; /* broadcast >= this uses scatter + multicast-allgather rounds (0 = never) */
-  uint32_t nvls_blocks;        /* CTAs of the NVLS kernels (0 = max_blocks) */
-  uint32_t reserved0;
+  uint32_t nvls_blocks;        /* CTAs of the zero-copy NVLS kernel (0 = max_blocks) */
+  uint32_t nvls_lanes;         /* lane kernel: lanes (each 1 switch CTA + (max_blocks / lanes - 1 <= 7) copy CTAs) */
+  uint64_t lane_granule_bytes; /* lane kernel: bytes of one rank chunk's granule per round (multiple of 8 KiB) */
+  uint64_t nvls_lanes_min_bytes; /* AUTO: staged NVLS messages >= this use the lane kernel (0 = never) */
 } b200c_config_t;
 
 typedef struct {

@@ -311,7 +311,7 @@ def test_nvls_allreduce(raw_world, dtype):
     if not all(get([a.has_multicast.remote() for a in actors])):
         pytest.skip("multicast object not bound on this box")
     for n in (16, 100_003, 3_000_001):
-        for symmetric, algo in ((False, N.ALGO_NVLS), (True, N.ALGO_NVLS), (False, N.ALGO_NVLS_PIPE)):
+        for symmetric, algo in ((False, N.ALGO_NVLS), (True, N.ALGO_NVLS), (False, N.ALGO_NVLS_PIPE), (False, N.ALGO_NVLS_LANES)):
             if symmetric and (n * torch.empty((), dtype=dtype).element_size()) % 16:
                 continue
             outs = get([a.allreduce.remote(dtype, n, N.SUM, algo, None, symmetric) for a in actors])
@@ -354,9 +354,18 @@ def test_nvls_pipelined_multi_piece_and_fused(raw_world):
     assert torch.allclose(outs[0], want, rtol=1e-5, atol=4e-5)
     for r in range(1, W):
         assert_equal_bits(outs[r], outs[0], "every rank must hold identical bits")
-    outs = get([a.allreduce.remote(torch.float32, n, N.SUM, N.ALGO_NVLS_PIPE, torch.bfloat16) for a in actors])
-    want = O.allreduce_scaled([make_input(torch.float32, n, r) for r in range(W)], torch.bfloat16, 1.0 / W)
-    assert torch.allclose(outs[0], want, rtol=2e-2, atol=2e-2)
+    for algo in (N.ALGO_NVLS_PIPE, N.ALGO_NVLS_LANES):
+        outs = get([a.allreduce.remote(torch.float32, n, N.SUM, algo, torch.bfloat16) for a in actors])
+        want = O.allreduce_scaled([make_input(torch.float32, n, r) for r in range(W)], torch.bfloat16, 1.0 / W)
+        assert torch.allclose(outs[0], want, rtol=2e-2, atol=2e-2)
+        for r in range(1, W):
+            assert_equal_bits(outs[r], outs[0], "every rank must hold identical bits")
+    # lane kernel: one launch for a message several times the staging half (8 MiB here), many ring rounds, 20 in a row
+    n = 9_000_017
+    for _ in range(20):
+        outs = get([a.allreduce.remote(torch.float32, n, N.SUM, N.ALGO_NVLS_LANES) for a in actors])
+    want = O.allreduce([make_input(torch.float32, n, r) for r in range(W)])
+    assert torch.allclose(outs[0], want, rtol=1e-5, atol=4e-5)
     for r in range(1, W):
         assert_equal_bits(outs[r], outs[0], "every rank must hold identical bits")
 

@@ -29,6 +29,7 @@ class Violation(AssertionError):
 
 class World:
     ROUNDS = 3   # rounds per block of the round-pipelined kernels
+    LANE_SLOTS = 3   # staging ring slots of the lane kernel (csrc kLaneSlots)
 
     def __init__(self, W, B, ops, use_arrive_rule=True):
         self.W, self.B, self.ops, self.rule = W, B, ops, use_arrive_rule
@@ -37,6 +38,7 @@ class World:
         self.flagB = [[[0] * W for _ in range(B)] for _ in range(W)]
         self.pipeA = [[[0] * W for _ in range(B)] for _ in range(W)]    # per-round flags of the pipelined kernels
         self.pipeB = [[[0] * W for _ in range(B)] for _ in range(W)]
+        self.laneIn = [[0] * B for _ in range(W)]                        # lane kernel: copy CTA k -> switch CTA (local)
         self.content = {}     # region -> seq of the data it holds
         self.pending = {}     # region -> set of (rank, block) that still have to read that data
         self.op_idx = [0] * W                                            # kernel each rank is in
@@ -54,7 +56,7 @@ class World:
         st = []
         R = self.ROUNDS
         # host-side counters every rank advances identically: round-flag epoch and LL op number
-        e = R * sum(1 for kk, _ in self.ops[:k] if kk in ("nvls_rounds", "bcast_rounds"))
+        e = R * sum(1 for kk, _ in self.ops[:k] if kk in ("nvls_rounds", "bcast_rounds", "nvls_lanes"))
         ll_no = 1 + sum(1 for kk, _ in self.ops[:k] if kk == "ll")
         if kind == "ll":
             # no prologue wait; data and flag travel together; arrive is published last
@@ -111,6 +113,32 @@ class World:
                 if x >= 1:
                     st += stage_out(x - 1)
             st += stage_out(R - 1)
+        elif kind == "nvls_lanes":
+            # one lane: block 0 is the switch CTA, blocks 1..B-1 are copy CTAs; the staging ring has 3 slots that are
+            # rewritten every three rounds (k_allreduce_nvls_lanes).  Regions: ("ring", slot, chunk, share k).
+            Kc = self.B - 1
+            if Kc == 0:
+                return st  # a lane needs at least one copy CTA; the host never launches such a grid
+            tag = lambda x: (q, x)  # noqa: E731  data of round x of this op
+            if b == 0:
+                for x in range(R):
+                    st += [("wait_lane_in", kk, e + x + 1) for kk in range(Kc)]
+                    st += [("sigPA0", j, e + x + 1) for j in peers] + [("waitPA0", j, e + x + 1) for j in peers]
+                    st += [("read", (j, h, ("ring", x % self.LANE_SLOTS, r, kk), 0), tag(x)) for j in everyone for kk in range(Kc)]
+                    # the switch writes the reduced chunk r back into every rank's slot: the next readers are that
+                    # rank's copy CTAs (copy-out)
+                    st += [("write", (j, h, ("ring", x % self.LANE_SLOTS, r, kk), 0), ("red", q, x), {(j, kk + 1)}) for j in everyone for kk in range(Kc)]
+                    st += [("sigPB0", j, e + x + 1) for j in everyone]
+            else:
+                kk = b - 1
+                for x in range(R + 2):
+                    if x < R:
+                        # my share of every chunk's granule; readers: the switch CTA (block 0) of the chunk's owner
+                        st += [("write", (r, h, ("ring", x % self.LANE_SLOTS, j, kk), 0), tag(x), {(j, 0)}) for j in everyone]
+                        st += [("set_lane_in", kk, e + x + 1)]
+                    if x >= 2:
+                        st += [("waitPB0", j, e + x - 1) for j in everyone]
+                        st += [("read", (r, h, ("ring", (x - 2) % self.LANE_SLOTS, j, kk), 0), ("red", q, x - 2)) for j in everyone]
         elif kind == "bcast_rounds":
             others = [j for j in everyone if j != root]
             if r == root:
@@ -164,6 +192,12 @@ class World:
             return self.pipeA[r][b][step[1]] >= step[2]
         if op == "waitPB":
             return self.pipeB[r][b][step[1]] >= step[2]
+        if op == "wait_lane_in":
+            return self.laneIn[r][step[1]] >= step[2]
+        if op == "waitPA0":
+            return self.pipeA[r][0][step[1]] >= step[2]
+        if op == "waitPB0":
+            return self.pipeB[r][0][step[1]] >= step[2]
         if op == "ll_read":  # the receiver polls the slot itself: ready once the flag of THIS op is there
             return self.content.get(step[1]) == step[2]
         return True
@@ -183,13 +217,32 @@ class World:
         elif op == "sigPB":
             assert s[2] > self.pipeB[s[1]][b][r], "round flags must increase monotonically"
             self.pipeB[s[1]][b][r] = s[2]
+        elif op == "set_lane_in":
+            assert s[2] > self.laneIn[r][s[1]]
+            self.laneIn[r][s[1]] = s[2]
+        elif op == "sigPA0":
+            assert s[2] > self.pipeA[s[1]][0][r]
+            self.pipeA[s[1]][0][r] = s[2]
+        elif op == "sigPB0":
+            assert s[2] > self.pipeB[s[1]][0][r]
+            self.pipeB[s[1]][0][r] = s[2]
         elif op == "write":
             region, q, readers = s[1], s[2], s[3]
             # Conservative aliasing: one-shot and two-shot lay slots and tiles out differently inside a
             # half, so a write may land on ANY older data of the same (rank, half).  Data of the same op
             # is disjoint by construction (distinct slot / tile per writer).
+            def op_of(tag):  # data tags of the lane kernel are (op, round) / ("red", op, round)
+                return tag if not isinstance(tag, tuple) else (tag[1] if tag[0] == "red" else tag[0])
+
+            ring = isinstance(region[2], tuple) and region[2][0] == "ring"
             for other, seq in self.content.items():
-                if other[:2] == region[:2] and seq != q and self.pending.get(other):
+                if ring and isinstance(other[2], tuple) and other[2][0] == "ring" and op_of(seq) == op_of(q):
+                    # same op, ring addressing is exact: only the very same slot/chunk/share aliases
+                    if other == region and seq != q and self.pending.get(other):
+                        raise Violation(f"S1: rank {r} block {b} overwrites ring region {region} (now {q}) while "
+                                        f"{sorted(self.pending[other])} still have to read {seq}")
+                    continue
+                if other[:2] == region[:2] and op_of(seq) != op_of(q) and self.pending.get(other):
                     raise Violation(f"S1: rank {r} block {b} op {q} writes {region} while {sorted(self.pending[other])} "
                                     f"still have to read op {seq} data in {other} of the same staging half")
             self.content[region], self.pending[region] = q, set(readers)
@@ -225,7 +278,7 @@ class World:
 
 
 def random_ops(rng, W, n):
-    kinds = ["twoshot", "oneshot", "nvls", "nvls_rounds", "ll", "broadcast", "bcast_rounds", "reduce", "barrier"]
+    kinds = ["twoshot", "oneshot", "nvls", "nvls_rounds", "nvls_lanes", "ll", "broadcast", "bcast_rounds", "reduce", "barrier"]
     return [(k, rng.randrange(W)) for k in (rng.choice(kinds) for _ in range(n))]
 
 
@@ -279,6 +332,32 @@ def test_mixed_algorithms_share_the_staging_safely():
     ops = [("twoshot", 0), ("broadcast", 1), ("oneshot", 0), ("reduce", 2), ("twoshot", 0), ("broadcast", 0), ("oneshot", 0)] * 3
     for slow in range(4):
         World(4, 2, ops).run(rng, lambda r, b: 0.02 if r == slow else 1.0)
+
+
+def test_lane_kernel_ring_reuse_is_safe_and_two_slots_would_not_be():
+    """The lane kernel rewrites a three-slot staging ring every three rounds.  Many rounds, a slow and a fast
+    rank, one to three copy CTAs per lane."""
+    rng = random.Random(31)
+    old = World.ROUNDS
+    World.ROUNDS = 7
+    try:
+        ops = [("nvls_lanes", 0), ("ll", 0), ("nvls_lanes", 0), ("broadcast", 1), ("nvls_lanes", 0), ("twoshot", 0)]
+        for W, B in ((2, 2), (3, 3), (4, 4), (8, 2)):
+            for slow in range(min(W, 2)):
+                for weight in (0.03, 25.0):
+                    World(W, B, ops).run(rng, lambda r, b: weight if r == slow else 1.0)
+        # teeth: with only two slots in(q) would overwrite the slot out(q-2) still has to read
+        World.LANE_SLOTS = 2
+        caught = 0
+        for _ in range(20):
+            try:
+                World(2, 2, [("nvls_lanes", 0)]).run(rng)
+            except Violation:
+                caught += 1
+        assert caught > 0
+    finally:
+        World.ROUNDS = old
+        World.LANE_SLOTS = 3
 
 
 def test_ll_and_round_pipelined_kernels_between_asymmetric_ops():
