@@ -205,7 +205,7 @@ extern "C" void b200c_default_config(b200c_config_t* cfg) {
   cfg->staging_bytes = 256ull << 20;
   cfg->symmetric_bytes = 0;
   cfg->p2p_slot_bytes = 32ull << 10;
-  cfg->p2p_slots = 256;
+  cfg->p2p_slots = 1024;   // 32 MiB per ordered pair: at ~500 GB/s the ring must hold the ~60 us of data a ready/ack round trip is behind
   cfg->max_blocks = 296;
   cfg->oneshot_max_bytes = 0;  // 0 = pick by world size in b200c_comm_create
   cfg->nvls_min_bytes = (1ull << 20) + 1;
@@ -322,10 +322,10 @@ extern "C" int b200c_comm_create(int rank, int world, int device, const b200c_co
   // layout
   c->off_staging = kPadBytes;
   c->off_p2p = c->off_staging + 2 * cfg.staging_bytes;
-  size_t p2p_bytes = world > 1 ? (size_t)kMaxRanks * cfg.p2p_slots * cfg.p2p_slot_bytes : 0;
+  size_t p2p_bytes = world > 1 ? (size_t)world * cfg.p2p_slots * cfg.p2p_slot_bytes : 0;   // one ring per source rank
   c->mcells = world > 2 ? (cfg.p2p_slots < 64 ? cfg.p2p_slots : 64) : 0;  // with one possible reader the pairwise ring is the multi-reader ring
   c->off_mring = round_up(c->off_p2p + p2p_bytes, 4096);
-  size_t mring_bytes = (size_t)kMaxRanks * c->mcells * cfg.p2p_slot_bytes;
+  size_t mring_bytes = (size_t)world * c->mcells * cfg.p2p_slot_bytes;
   c->off_ll = round_up(c->off_mring + mring_bytes, 4096);
   c->ll_words = world > 1 ? round_up((cfg.ll_max_bytes + 3) / 4, 4) : 0;   // whole 16-byte vectors
   size_t ll_bytes = 2 * (size_t)kMaxRanks * c->ll_words * 8;
@@ -791,7 +791,7 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     static const bool use_tma = [] { const char* e = getenv("B200COLL_LOCAL_SCALE_TMA"); return !e || e[0] != '0'; }();
     size_t tma_elems = 0;
     if (use_tma && count * esz >= (1u << 20) && ((uintptr_t)send & 15) == 0 && ((uintptr_t)recv & 15) == 0 &&
-        (dtype == B200C_FLOAT32 || dtype == B200C_BFLOAT16 || dtype == B200C_FLOAT16)) {
+        (dtype == B200C_FLOAT32 || ((dtype == B200C_BFLOAT16 || dtype == B200C_FLOAT16) && wire == dtype))) {
       size_t ntiles = count * esz / kTmaTileBytes;
       tma_elems = ntiles * kTmaTileBytes / esz;
       if (c->tma_ctas_per_sm == 0) {
@@ -821,6 +821,18 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
       a.n = count - tma_elems;
     }
     int grid = local_scale_grid<float, bf16_t>(c, a.n * esz);
+    switch (dtype * 16 + wire) {
+      case B200C_FLOAT32 * 16 + B200C_FLOAT32: k_local_scale<float, float><<<grid, kThreads, 0, s>>>(a); break;
+      case B200C_FLOAT32 * 16 + B200C_BFLOAT16: k_local_scale<float, bf16_t><<<grid, kThreads, 0, s>>>(a); break;
+      case B200C_FLOAT32 * 16 + B200C_FLOAT16: k_local_scale<float, f16_t><<<grid, kThreads, 0, s>>>(a); break;
+      case B200C_BFLOAT16 * 16 + B200C_BFLOAT16: k_local_scale<bf16_t, bf16_t><<<grid, kThreads, 0, s>>>(a); break;
+      case B200C_FLOAT16 * 16 + B200C_FLOAT16: k_local_scale<f16_t, f16_t><<<grid, kThreads, 0, s>>>(a); break;
+      case B200C_FLOAT64 * 16 + B200C_FLOAT64: k_local_scale<double, double><<<grid, kThreads, 0, s>>>(a); break;
+      default:
+        // integer AVG over one rank is the identity
+        if (send != recv) RT(cudaMemcpyAsync(recv, send, count * esz, cudaMemcpyDeviceToDevice, s));
+        return B200C_OK;
+    }
     return launch_check(c, "local_scale");
   }
 
@@ -906,6 +918,7 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
         if (tb > want) tb = want;
         size_t ring = (size_t)L * kLaneSlots * W * tb;
         while (ring > c->cfg.staging_bytes && tb > 8192) { tb -= 8192; ring = (size_t)L * kLaneSlots * W * tb; }
+        while (ring > c->cfg.staging_bytes && L > 1) { L--; ring = (size_t)L * kLaneSlots * W * tb; }   // a small staging area: fewer lanes
         if (ring > c->cfg.staging_bytes) return fail(B200C_EINVAL, "staging_bytes too small for the lane kernel's ring (%zu bytes)", ring);
         a.tile = tb / wsz;
         a.lane_copy = (int)Kc;

@@ -191,8 +191,20 @@ __global__ void __launch_bounds__(kLLThreads) k_allreduce_ll(const __grid_consta
   }
   // arrival (the op after this one may start: arrive rule) goes last so that the fence of the release
   // does not sit in front of the data stores
-  if (blockIdx.x == 0 && t < c.world && t != c.rank)
+  if (blockIdx.x == 0 && t < c.world && t != c.rank) {
     st_release_sys(reinterpret_cast<uint32_t*>(c.arena[t] + kOffArrive) + c.rank, a.seq);
+    // a rank whose message is the SHORTER one receives everything it waits for and would not notice a
+    // peer that passed other arguments: compare the announcement that peer made at the start of its kernel
+    // (no waiting: if it has not landed yet the check is skipped, the longer side reports the mismatch)
+    const unsigned long long* sl = reinterpret_cast<const unsigned long long*>(c.arena[c.rank] + kOffOpSig) + (a.seq & 1) * 8 + t;
+    unsigned long long sv;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(sv) : "l"(sl) : "memory");
+    if ((uint32_t)(sv >> 32) == a.seq && (uint32_t)sv != a.sig) {
+      if (c.status->error == 0) { c.status->err_a = (uint32_t)sv; c.status->err_b = a.sig; }
+      record_error(c.status, B200C_EMISMATCH, a.seq, t, 5);
+      c.status->abort_flag = 1;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -288,6 +288,19 @@ def time_back_to_back(fn, bufs, iters, dist, world, rounds=3):
     return best
 
 
+def time_torch_copy_same_size(nbytes, dist, world):
+    """torch's own out-of-place copy of the same number of bytes, back to back (read nbytes + write nbytes): what a
+    plain STREAM-style kernel reaches at THIS size — the driver's MEASURED_PEAKS figure is a 2 GiB copy, whose
+    ramp-up and launch gap are amortised over ~650 us instead of ~10 us."""
+    import torch
+
+    n = nbytes // 4
+    src = [torch.randn(n, device="cuda") for _ in range(4)]
+    dst = [torch.empty(n, device="cuda") for _ in range(4)]
+    us = time_back_to_back(lambda i: dst[i].copy_(src[i]), list(range(4)), 40, dist, world)
+    return 2 * nbytes / (us * 1e-6) / 1e9
+
+
 def time_fused_bucket(comm, dist, world, wire):
     """The fused gradient kernel alone (full grid, nothing else on the GPU) on ResNet-50's largest bucket
     (30 MiB fp32), in place, rotating over 8 buckets (240 MiB > L2).  Microseconds per launch, back to back."""
@@ -652,7 +665,8 @@ def run_ddp_grad_parity(dist, world, rank, device):
                 ref = ref16.float()
             for p_, gview in zip(bucket.parameters(), bucket.gradients()):
                 off = gview.storage_offset() - buf.storage_offset()
-                expected[p_] = ref[off:off + gview.numel()].view_as(p_)
+                # same sizes/strides as the bucket view (channels_last parameters are stored in memory order)
+                expected[p_] = ref.as_strided(gview.size(), gview.stride(), off)
             return ddp_hook.b200_allreduce_hook(st, bucket)
 
         m.register_comm_hook(state, both)
@@ -951,7 +965,7 @@ def main():
 
     # ---- collectives: parity, p2p, sweeps
     sweep = collectives = p2p = parity = None
-    fused_alone = None
+    fused_alone = copy_same_size = None
     if world > 1:
         from ant_ray_b200.b200_group import PeerMemoryComm, make_config, next_comm_key
 
@@ -988,6 +1002,7 @@ def main():
         log("allreduce sweep (loopback)")
         try:
             fused_alone = time_fused_bucket(state.comm, dist, world, args.wire)
+            copy_same_size = time_torch_copy_same_size(30 << 20, dist, world)
             sweep = run_sweep_loopback(args.sweep_max_bytes)
         except Exception as e:  # noqa: BLE001
             optional_errors["allreduce_sweep"] = repr(e)[:300]
@@ -1027,6 +1042,8 @@ def main():
                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture "
                                     "(profiles/r02_ncu_full_1gpu_details.txt); the written half is still dirty in L2 at kernel end",
                     "launch_us": round(t_us, 2), "algorithmic_bytes": int(alg),
+                    "torch_copy_same_bytes_gbs": round(copy_same_size, 1) if copy_same_size else None,
+                    "frac_of_torch_copy_same_bytes": round(ach / copy_same_size, 3) if copy_same_size else None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"}
 
         # `roofline`: the kernel timed alone, back to back (what the burst peak is comparable with);

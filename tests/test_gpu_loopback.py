@@ -221,7 +221,7 @@ def test_broadcast_and_reduce(world):
 
 def test_send_recv(world):
     W = world.world_size
-    for nbytes in (1, 100_000, (32 << 10) * 300 + 17):  # the last one wraps the 256-cell ring
+    for nbytes in (1, 100_000, (32 << 10) * 1100 + 17):  # the last one wraps the 1024-cell ring
         src = torch.randint(0, 255, (nbytes,), dtype=torch.uint8, generator=torch.Generator().manual_seed(7))
         d_src = src.cuda()
         d_dst = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")

@@ -294,7 +294,7 @@ def test_wrong_shape_raises_channel_error_not_hang(pair, blocking):
     e = pair(2, blocking_errors=blocking, timeout_ms=5000)
 
     def step(r):
-        x = torch.ones(1000 * (r + 1), device="cuda")
+        x = torch.ones(100_000 * (r + 1), device="cuda")   # beyond the LL range: both ranks see the mismatch in the flag round
         try:
             e.comms[r].allreduce(x, torch.empty_like(x))
         except RayChannelError as err:
