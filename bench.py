@@ -562,6 +562,7 @@ def run_parity(comm, dist, world, rank, device, wire):
     if comm.multicast:
         check_allreduce("nvls_staged", N.ALGO_NVLS, 3_000_001, use_int=False)
         check_allreduce("nvls_rounds", N.ALGO_NVLS_PIPE, (16 << 20) + 4, use_int=False)
+        check_allreduce("nvls_lanes", N.ALGO_NVLS_LANES, (24 << 20) + 12, use_int=False)
         check_allreduce("nvls_symmetric", N.ALGO_NVLS, 4 << 20, use_int=False, sym=True)
     # fused gradient mean, 16-bit wire: against the reference's own formulation (bf16_compress_hook:
     # buffer.to(bf16).div_(W) -> allreduce -> copy back, torch default_hooks.py)
@@ -665,8 +666,7 @@ def run_ddp_grad_parity(dist, world, rank, device):
                 ref = ref16.float()
             for p_, gview in zip(bucket.parameters(), bucket.gradients()):
                 off = gview.storage_offset() - buf.storage_offset()
-                # same sizes/strides as the bucket view (channels_last parameters are stored in memory order)
-                expected[p_] = ref.as_strided(gview.size(), gview.stride(), off)
+                expected[p_] = ref[off:off + gview.numel()]   # the bucket holds every gradient in the parameter's MEMORY order
             return ddp_hook.b200_allreduce_hook(st, bucket)
 
         m.register_comm_hook(state, both)
@@ -676,7 +676,10 @@ def run_ddp_grad_parity(dist, world, rank, device):
         torch.cuda.synchronize()
         state.comm.check()
         params = [p_ for p_ in m.parameters() if p_.grad is not None]
-        num = max(float((p_.grad - expected[p_]).abs().max().item()) for p_ in params)
+        def flat(t):  # dense tensors (contiguous or channels_last): the elements in memory order
+            return t.as_strided((t.numel(),), (1,), t.storage_offset())
+
+        num = max(float((flat(p_.grad) - expected[p_]).abs().max().item()) for p_ in params)
         den = max(float(expected[p_].abs().max().item()) for p_ in params)
         tol = 1e-5 if wire == "fp32" else 2 ** -6
         out["ddp_grads_%s_wire" % wire] = {"max_rel_err_vs_stock_ddp": num / den, "n_params": len(params), "n_buckets_launches": state.launches,
@@ -734,6 +737,94 @@ def run_comm_bound(args, dist, world, device, steps=30, warmup=8):
         torch.cuda.empty_cache()
         rows.append(row)
     return rows
+
+
+# ------------------------------------------------------------------------------------------------
+# RLlib-shaped learner update (BASELINE config 5): KB-scale gradients, latency-bound
+# ------------------------------------------------------------------------------------------------
+def run_ppo_shape(dist, world, rank, device, steps=200, warmup=30):
+    """RLlib's TorchLearner wraps the RLModule in DistributedDataParallel when num_learners > 1
+    (rllib/core/learner/torch/torch_learner.py:533-553, `TorchDDPRLModule(module, **torch_ddp_kwargs)`), so a PPO
+    learner's gradient reduction is one DDP bucket of a few hundred KB per update.  Model: RLlib's default PPO
+    MLP (fcnet_hiddens [256, 256], separate value tower) on a CartPole-sized problem, minibatch 128, Adam.
+    (a) DDP + our hook vs stock NCCL DDP: learner updates per second.  (b) the same gradient set reduced tensor
+    by tensor through the ray.util.collective API (`collective.allreduce(tensor, group)`, the pattern of
+    actor code that averages gradients by hand) vs torch.distributed.all_reduce on NCCL: microseconds per set."""
+    import torch
+    import torch.nn as nn
+    from torch.nn.parallel import DistributedDataParallel
+
+    from ant_ray_b200 import collective as col
+    from ant_ray_b200 import ddp_hook
+
+    def make():
+        torch.manual_seed(0)
+
+        class PPOModule(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.pi = nn.Sequential(nn.Linear(4, 256), nn.Tanh(), nn.Linear(256, 256), nn.Tanh(), nn.Linear(256, 2))
+                self.vf = nn.Sequential(nn.Linear(4, 256), nn.Tanh(), nn.Linear(256, 256), nn.Tanh(), nn.Linear(256, 1))
+
+            def forward(self, obs):
+                return self.pi(obs), self.vf(obs)
+
+        return PPOModule().to(device)
+
+    obs = torch.randn(128, 4, device=device)
+    adv = torch.randn(128, device=device)
+
+    def make_step(m, opt):
+        def step():
+            logits, v = m(obs)
+            loss = -(torch.log_softmax(logits, -1)[:, 0] * adv).mean() + 0.5 * (v.squeeze(-1) - adv).pow(2).mean()
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        return step
+
+    out = {"model": "PPO MLP 4-256-256-{2,1}, minibatch 128, Adam", "grad_bytes": sum(p.numel() for p in make().parameters()) * 4}
+
+    def rate(step):
+        for _ in range(warmup):
+            step()
+        fence(dist, world)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0, dist, world)
+        return steps / dt
+
+    m = DistributedDataParallel(make(), device_ids=[device], output_device=device)
+    state = ddp_hook.register(m, wire="fp32", name="ppo")
+    out["b200_hook_updates_per_s"] = round(rate(make_step(m, torch.optim.Adam(m.parameters(), lr=3e-4))), 1)
+    state.comm.check()
+    state.comm.destroy()
+    del m
+    m = DistributedDataParallel(make(), device_ids=[device], output_device=device)
+    out["nccl_ddp_updates_per_s"] = round(rate(make_step(m, torch.optim.Adam(m.parameters(), lr=3e-4))), 1)
+    del m
+    # (b) per-tensor allreduce through the ray.util.collective surface
+    grads = [torch.randn_like(p) for p in make().parameters()]
+    name = "ppo-manual"
+    col.init_collective_group(world, rank, backend="b200", group_name=name)
+
+    def ours():
+        for g in grads:
+            col.allreduce(g, name)
+
+    def nccl():
+        for g in grads:
+            dist.all_reduce(g)
+
+    for tag, fn in (("b200_collective_api", ours), ("nccl_all_reduce", nccl)):
+        us = time_back_to_back(lambda _: fn(), [None], 50, dist, world, rounds=2)
+        out[tag + "_us_per_gradient_set"] = round(us, 1)
+    out["tensors_per_set"] = len(grads)
+    col.get_group_handle(name).check(synchronize=True)
+    col.destroy_collective_group(name)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -955,13 +1046,18 @@ def main():
     del model, opt, step
     torch.cuda.empty_cache()
 
-    comm_bound = None
+    comm_bound = ppo = None
     if world > 1 and not args.no_comm_bound:
         log("comm-bound rows (batch 32)")
         try:
             comm_bound = run_comm_bound(args, dist, world, device)
         except Exception as e:  # noqa: BLE001
             optional_errors["comm_bound"] = repr(e)[:300]
+        log("RLlib-shaped learner update")
+        try:
+            ppo = run_ppo_shape(dist, world, rank, device)
+        except Exception as e:  # noqa: BLE001
+            optional_errors["rllib_ppo_shape"] = repr(e)[:300]
 
     # ---- collectives: parity, p2p, sweeps
     sweep = collectives = p2p = parity = None
@@ -1080,6 +1176,7 @@ def main():
                           "nccl_version": ".".join(map(str, torch.cuda.nccl.version()))},
             "multicast": multicast,
             "comm_bound": comm_bound,
+            "rllib_ppo_shape": ppo,
             "parity": parity,
             "p2p": p2p,
             "allreduce_sweep": sweep,
