@@ -192,3 +192,116 @@ def test_pipe_meta_channel():
     assert r.read(1) == [TorchTensorMetadata((1, 2), torch.int32)]
     with pytest.raises(TimeoutError):
         r.read(0.01)
+
+
+class InlineCommunicator(QueueCommunicator):
+    """CPU double of a communicator that, like B200Communicator, carries tensor headers itself (N3) and can
+    deliver one payload to several readers (N2).  Headers and payloads travel through the same queues."""
+
+    inline_metadata = True
+    multi_reader = True
+
+    def __init__(self, rank, queues, mqueues):
+        super().__init__(rank, queues)
+        self.mq = mqueues       # (src, dst) -> queue of multi-reader payloads
+        self.multi_sends = 0
+        self.headers = 0
+
+    def send_multi(self, value, peer_ranks):
+        self.multi_sends += 1
+        for p in peer_ranks:
+            self.mq[(self.rank, p)].put(value.clone())
+
+    def recv_multi(self, shape, dtype, peer_rank, allocator=None):
+        t = self.mq[(peer_rank, self.rank)].get(timeout=5)
+        assert tuple(t.shape) == tuple(shape) and t.dtype == dtype
+        buf = allocator(shape, dtype)
+        buf.copy_(t)
+        return buf
+
+    def send_with_header(self, buf, peer_ranks, index=0, count=1):
+        peers = [peer_ranks] if isinstance(peer_ranks, int) else list(peer_ranks)
+        for p in peers:
+            self.headers += 1
+            self.queues[(self.rank, p)].put(("hdr", tuple(buf.shape), buf.dtype, index, count))
+        if len(peers) == 1:
+            self.send(buf, peers[0])
+        else:
+            self.send_multi(buf, peers)
+
+    def announce_empty(self, peer_ranks):
+        for p in ([peer_ranks] if isinstance(peer_ranks, int) else list(peer_ranks)):
+            self.headers += 1
+            self.queues[(self.rank, p)].put(("hdr", (), torch.uint8, 0, 0))
+
+    def recv_with_header(self, peer_rank, allocator=None, timeout=None, multi=False):
+        tag, shape, dtype, index, count = self.queues[(peer_rank, self.rank)].get(timeout=5)
+        assert tag == "hdr"
+        if count == 0:
+            return None, 0, 0
+        fn = self.recv_multi if multi else self.recv
+        return fn(shape, dtype, peer_rank, allocator), index, count
+
+
+def make_inline(readers=(1,), static_shape=False, **kw):
+    queues = {(0, r): queue.Queue() for r in readers}
+    mqueues = {(0, r): queue.Queue() for r in readers}
+    side = ListMeta()
+    w = TensorListChannel(InlineCommunicator(0, queues, mqueues), 0, list(readers), side, static_shape, cpu_alloc, require_cuda=False, **kw)
+    rs = [TensorListChannel(InlineCommunicator(r, queues, mqueues), 0, list(readers), side, static_shape, cpu_alloc, require_cuda=False, **kw)
+          for r in readers]
+    return w, rs, side
+
+
+def test_inline_headers_replace_the_metadata_channel():
+    """N3: with a communicator that carries headers, dynamic shapes never touch the side channel
+    (reference torch_tensor_accelerator_channel.py:574-578, 592-608)."""
+    w, (r,), side = make_inline()
+    for shape in [(10,), (3, 4), (0,), (2, 2, 2)]:
+        a, b = torch.randn(shape), torch.arange(3)
+        w.write([a, b])
+        ga, gb = r.read()
+        assert torch.equal(ga, a) and torch.equal(gb, b)
+    w.write([])                      # an empty list still announces itself
+    assert r.read() == []
+    assert side.writes == 0 and side.reads == 0 and w._comm.headers == 9
+
+
+def test_inline_static_shape_sends_headers_once():
+    w, (r,), side = make_inline(static_shape=True)
+    for i in range(4):
+        t = torch.full((7,), float(i))
+        w.write([t])
+        assert torch.equal(r.read()[0], t)
+    assert w._comm.headers == 1 and side.writes == 0
+    with pytest.raises(ValueError):
+        w.write([torch.zeros(8)])
+
+
+def test_multi_reader_channel_sends_each_tensor_once():
+    """N2: one send_multi per tensor instead of one send per reader (reference :586-590 TODO)."""
+    w, rs, side = make_inline(readers=(1, 2, 3))
+    a, b = torch.arange(6).reshape(2, 3), torch.ones(4, dtype=torch.bfloat16)
+    w.write([a, b])
+    for r in rs:
+        ga, gb = r.read()
+        assert torch.equal(ga, a) and torch.equal(gb, b)
+    assert w._comm.multi_sends == 2 and w._comm.sent == 0 and w._comm.headers == 6
+    # static shapes: later messages are bare multi-sends
+    w2, rs2, _ = make_inline(readers=(1, 2), static_shape=True)
+    for i in range(3):
+        w2.write([torch.full((5,), float(i))])
+        for r in rs2:
+            assert torch.equal(r.read()[0], torch.full((5,), float(i)))
+    assert w2._comm.multi_sends == 3 and w2._comm.headers == 2
+
+
+def test_multicast_and_inlining_can_be_switched_off_per_channel():
+    w, rs, side = make_inline(readers=(1, 2), multicast=False, inline_metadata=False)
+    t = torch.randn(6)
+    w.write([t])
+    # the side channel carries the metadata once per reader read, the payload goes out once per reader
+    for r in rs:
+        side.q.put([TorchTensorMetadata((6,), torch.float32)]) if side.q.empty() else None
+        assert torch.equal(r.read()[0], t)
+    assert w._comm.sent == 2 and w._comm.multi_sends == 0 and w._comm.headers == 0 and side.writes == 1
