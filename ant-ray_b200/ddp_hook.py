@@ -52,13 +52,28 @@ class B200GradState:
         return out
 
 
+SMALL_BUCKET_BYTES = 1 << 20
+
+
 def b200_allreduce_hook(state: B200GradState, bucket) -> torch.futures.Future[torch.Tensor]:
     buf = bucket.buffer()
     if buf.dtype not in _BUCKET:
         raise RuntimeError(f"B200 gradient hook supports fp32 / bf16 / fp16 buckets, got {buf.dtype}")
     dtype = _BUCKET[buf.dtype]
     wire = state.wire if (state.wire is not None and buf.dtype == torch.float32) else dtype
-    comm, s = state.comm, state.stream
+    comm = state.comm
+    nbytes = buf.numel() * buf.element_size()
+    if nbytes <= SMALL_BUCKET_BYTES and not state.time_kernels:
+        # Latency-bound buckets (an RLlib learner's few hundred KB): nothing to overlap, so the reduction is enqueued
+        # on the stream the gradients were produced on — no stream switch, no extra events — and takes the LL / one-shot
+        # kernels with an fp32 wire (a 16-bit wire would only add a cast pass to a message this small).
+        comm.allreduce_scaled(buf.data_ptr(), buf.data_ptr(), buf.numel(), dtype, dtype, 1.0 / comm.world_size, state.algo)
+        fut = torch.futures.Future(devices=[torch.device("cuda", comm.device)])
+        fut.set_result(buf)
+        state.launches += 1
+        state.bytes += nbytes
+        return fut
+    s = state.stream
     s.wait_stream(torch.cuda.current_stream(comm.device))  # gradients of this bucket are final
     with torch.cuda.stream(s):
         if state.time_kernels:
@@ -68,11 +83,11 @@ def b200_allreduce_hook(state: B200GradState, bucket) -> torch.futures.Future[to
         comm.allreduce_scaled(buf.data_ptr(), buf.data_ptr(), buf.numel(), dtype, wire, 1.0 / comm.world_size, state.algo)
         if state.time_kernels:
             e1.record(s)
-            state.events.append((e0, e1, buf.numel() * buf.element_size()))
+            state.events.append((e0, e1, nbytes))
         fut = torch.futures.Future(devices=[torch.device("cuda", comm.device)])
         fut.set_result(buf)  # records an event on `s`; DDP's wait() makes the compute stream wait on it
     state.launches += 1
-    state.bytes += buf.numel() * buf.element_size()
+    state.bytes += nbytes
     return fut
 
 
@@ -91,7 +106,8 @@ def make_grad_state(world_size: Optional[int] = None, rank: Optional[int] = None
         # (the bucket traffic needs a tiny fraction of NVLink), like NCCL's handful of channels.
         from .b200_group import make_config
 
-        config = make_config(max_blocks=int(os.environ.get("B200COLL_HOOK_MAX_BLOCKS", "32")))
+        # 64 CTAs: 1.07 ms of hook time per ResNet-50 step at 8 GPUs against 2.04 ms with 32 (profiles/r02_bench_8gpu*.json)
+        config = make_config(max_blocks=int(os.environ.get("B200COLL_HOOK_MAX_BLOCKS", "64")))
     comm = PeerMemoryComm(world_size, rank, next_comm_key("train/" + name), device, store, config)
     return B200GradState(comm, wire=wire, **kw)
 

@@ -45,9 +45,9 @@ RESNET50_PARAMS = 25_557_032
 NVLINK_PEAK_MEASURED = 770.0   # GB/s per direction per GPU, peer copy (B200_PROFILING.md)
 NVLINK_PEAK_NOMINAL = 900.0
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the N = 1 roofline kernel, from the committed
-# `ncu --set full` capture (profiles/r02_ncu_full_1gpu_details.txt: k_local_scale<float, bf16_t>, 30 MiB bucket):
+# `ncu --set full` capture (profiles/r02_ncu_full_local_scale_tma_details.txt: k_local_scale_tma<float, bf16_t>, 30 MiB bucket):
 # 31.47 MB read; the 31.46 MB written are still dirty in the 126 MB L2 when the kernel ends (ncu: 0.00 MB)
-NCU_TRAFFIC_LOCAL_SCALE_30MIB = 31_468_544 + 4_096
+NCU_TRAFFIC_LOCAL_SCALE_30MIB = 31_465_216 + 1_792_000   # read + write of the second of four captured launches
 
 
 def log(msg):
@@ -1132,11 +1132,11 @@ def main():
             alg = nelem * 8  # read fp32 + write fp32
             ach = alg / (t_us * 1e-6) / 1e9
             peak = peaks.get("hbm_gbs", 6650.0)
-            return {"bound": "hbm", "kernel": f"k_local_scale<float, bf16_t>: fused gradient scale / wire rounding (world=1), {nelem * 4 >> 20} MiB fp32 bucket, {where}",
+            return {"bound": "hbm", "kernel": f"k_local_scale_tma<float, {args.wire}>: fused gradient scale / wire rounding (world=1), {nelem * 4 >> 20} MiB fp32 bucket, {where}",
                     "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 3),
                     "traffic": NCU_TRAFFIC_LOCAL_SCALE_30MIB if nelem == (30 << 18) else None,
                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture "
-                                    "(profiles/r02_ncu_full_1gpu_details.txt); the written half is still dirty in L2 at kernel end",
+                                    "(profiles/r02_ncu_full_local_scale_tma_details.txt); the written half is still dirty in L2 at kernel end",
                     "launch_us": round(t_us, 2), "algorithmic_bytes": int(alg),
                     "torch_copy_same_bytes_gbs": round(copy_same_size, 1) if copy_same_size else None,
                     "frac_of_torch_copy_same_bytes": round(ach / copy_same_size, 3) if copy_same_size else None,
