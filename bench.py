@@ -939,7 +939,11 @@ def run_reference(args):
     if rank != 0:
         return
     world = max(1, args.gpus)
-    batch = int(os.environ.get("BENCH_CPU_BATCH", 16))  # bounded sample: small per-worker batch
+    # N = 1: the b200 arm's own per-GPU batch (same config; the time budget bounds the number of steps instead).
+    # N > 1: W gloo workers share the host's cores and memory, so the per-worker batch is cut to keep the whole
+    # job at ~one batch of images in flight; that line's `config` says what it ran.
+    default_batch = args.batch if world == 1 else max(16, args.batch // world)
+    batch = int(os.environ.get("BENCH_CPU_BATCH", default_batch))
     ips, sps, cores, done, cpu_dtype = cpu_reference(world, batch, args.steps, args.warmup, budget_s=float(os.environ.get("BENCH_CPU_BUDGET_S", 150)))
     sample = f"{world} gloo worker(s) x batch {batch}, {done} steps after <= {args.warmup} warm-up, torch DDP default reducer, {cpu_dtype}"
     cfg = workload_config(batch, world, "fp32")   # the batch this arm really ran
