@@ -44,7 +44,8 @@ class Config(Structure):
                 ("max_blocks", c_uint32), ("oneshot_max_bytes", c_uint64), ("nvls_min_bytes", c_uint64),
                 ("nvls_pipe_min_bytes", c_uint64), ("timeout_ms", c_uint64), ("granule_bytes", c_uint64),
                 ("ll_max_bytes", c_uint64), ("bcast_rounds_min_bytes", c_uint64), ("nvls_blocks", c_uint32),
-                ("nvls_lanes", c_uint32), ("lane_granule_bytes", c_uint64), ("nvls_lanes_min_bytes", c_uint64)]
+                ("nvls_lanes", c_uint32), ("lane_granule_bytes", c_uint64), ("nvls_lanes_min_bytes", c_uint64),
+                ("nvls_unroll", c_uint32), ("rounds_order", c_uint32)]
 
 
 class Props(Structure):

@@ -214,6 +214,8 @@ extern "C" void b200c_default_config(b200c_config_t* cfg) {
   cfg->granule_bytes = 32ull << 10;
   cfg->ll_max_bytes = 64ull << 10;    // W=8: LL 12 us vs one-shot 13 us at 64 KiB, 15 vs 15 at 128 KiB (profiles/r02_sweep8_small.log)
   cfg->bcast_rounds_min_bytes = 4ull << 20;
+  cfg->nvls_unroll = 4;
+  cfg->rounds_order = 0;
   cfg->nvls_lanes = 48;
   cfg->lane_granule_bytes = 64ull << 10;
   cfg->nvls_lanes_min_bytes = 0;   // opt-in until measured on the target box
@@ -804,8 +806,11 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_local_scale_tma<float, bf16_t>, kTmaThreads, kTmaSmemBytes) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
         c->tma_ctas_per_sm = nb;
       }
+      // balanced persistent grid: every CTA gets the same number of tiles (1920 tiles on 444 resident CTAs would
+      // leave most CTAs idle while a few run a fifth tile: 384 CTAs x 5 tiles instead)
       size_t cap = (size_t)c->sm_count * c->tma_ctas_per_sm;
-      int tgrid = (int)(ntiles < cap ? ntiles : cap);
+      size_t per_cta = (ntiles + cap - 1) / cap;
+      int tgrid = (int)((ntiles + per_cta - 1) / per_cta);
       switch (dtype * 16 + wire) {
         case B200C_FLOAT32 * 16 + B200C_FLOAT32: k_local_scale_tma<float, float><<<tgrid, kTmaThreads, kTmaSmemBytes, s>>>(a); break;
         case B200C_FLOAT32 * 16 + B200C_BFLOAT16: k_local_scale_tma<float, bf16_t><<<tgrid, kTmaThreads, kTmaSmemBytes, s>>>(a); break;
@@ -869,6 +874,7 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     base_args(c, &a);
     a.in = in + done * esz; a.out = out + done * esz;
     a.has_scale = has_scale; a.scale = scale;
+    a.nvls_unroll = (int)c->cfg.nvls_unroll; a.rounds_order = (int)c->cfg.rounds_order;
     size_t n;
     int grid;
     uint32_t rounds = 0;

@@ -336,17 +336,18 @@ __device__ __forceinline__ void multimem_st16(void* p, uint4 v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// in-switch reduce of nv 16-byte vectors at multicast address `mc`, broadcast back in place
-template <typename TW>
-__device__ __forceinline__ void nvls_reduce_bcast(char* mc, size_t nv, const CollArgs& a) {
+// in-switch reduce of nv 16-byte vectors at multicast address `mc`, broadcast back in place.
+// U vectors are in flight per thread (a.nvls_unroll: 4 or 8): the staged kernels visit the switch in short
+// bursts between local copies, so each burst has to carry more bytes to keep the switch fed.
+template <typename TW, int U>
+__device__ __forceinline__ void nvls_reduce_bcast_u(char* mc, size_t nv, const CollArgs& a, size_t i) {
   constexpr int V = 16 / sizeof(TW);
-  size_t i = threadIdx.x;
-  for (; i + (kUnroll - 1) * kThreads < nv; i += kUnroll * kThreads) {
-    uint4 v[kUnroll];
+  for (; i + (U - 1) * kThreads < nv; i += U * kThreads) {
+    uint4 v[U];
 #pragma unroll
-    for (int u = 0; u < kUnroll; u++) v[u] = Multimem<TW>::ld_reduce(mc + (i + u * kThreads) * 16);
+    for (int u = 0; u < U; u++) v[u] = Multimem<TW>::ld_reduce(mc + (i + u * kThreads) * 16);
 #pragma unroll
-    for (int u = 0; u < kUnroll; u++) {
+    for (int u = 0; u < U; u++) {
       if (a.has_scale) {
         Pack16<TW> p; p.u = v[u];
 #pragma unroll
@@ -366,6 +367,11 @@ __device__ __forceinline__ void nvls_reduce_bcast(char* mc, size_t nv, const Col
     }
     multimem_st16(mc + i * 16, v);
   }
+}
+template <typename TW>
+__device__ __forceinline__ void nvls_reduce_bcast(char* mc, size_t nv, const CollArgs& a) {
+  if (a.nvls_unroll >= 8) nvls_reduce_bcast_u<TW, 8>(mc, nv, a, threadIdx.x);
+  else nvls_reduce_bcast_u<TW, kUnroll>(mc, nv, a, threadIdx.x);
 }
 // user tensor -> staging for the granule [g0, g1) of every rank chunk (zero-pad the last vector so the
 // switch reduces defined values)
@@ -480,6 +486,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_allreduce_nvls_rounds(const __g
       nvls_stage_in<TI, TW>(a, mine, in, lo_of(q + 1), hi_of(q + 1));
       round_signal(kOffPipeA, a.pipe_base + q + 2, c);
     }
+    if (a.rounds_order && q >= 1) {   // variant: copy round q-1 out BEFORE visiting the switch for round q
+      if (!round_wait(kOffPipeB, a.pipe_base + q, c, 2)) return;
+      nvls_stage_out<TI, TW>(a, mine, out, lo_of(q - 1), hi_of(q - 1));
+    }
     if (!round_wait(kOffPipeA, a.pipe_base + q + 1, c, 1)) return;
     {
       size_t lo = (size_t)r * a.chunk + lo_of(q);
@@ -487,7 +497,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_allreduce_nvls_rounds(const __g
       if (cnt) nvls_reduce_bcast<TW>(c.mc_arena + base_off + lo * sizeof(TW), (cnt + V - 1) / V, a);
     }
     round_signal(kOffPipeB, a.pipe_base + q + 1, c);
-    if (q >= 1) {
+    if (!a.rounds_order && q >= 1) {
       if (!round_wait(kOffPipeB, a.pipe_base + q, c, 2)) return;
       nvls_stage_out<TI, TW>(a, mine, out, lo_of(q - 1), hi_of(q - 1));
     }

@@ -86,6 +86,8 @@ struct CollArgs {
   uint32_t pipe_base;  // round-pipelined kernels: flag value of round q is pipe_base + q + 1
   uint32_t ll_seq;     // LL kernels: per-communicator LL op counter (flag value; half = ll_seq & 1)
   int lane_copy;       // lane kernel: copy CTAs per lane (each lane = 1 switch CTA + lane_copy copy CTAs)
+  int nvls_unroll;     // multimem vectors in flight per thread (4 or 8)
+  int rounds_order;    // rounds kernel: 1 = copy round q-1 out before the switch stage of round q
   int symmetric;   // NVLS: in/out already live at the same offset of the symmetric region
   size_t sym_off;  // arena offset of that buffer
   const void* in_ptrs[kMaxRanks];
