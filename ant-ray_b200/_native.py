@@ -32,7 +32,7 @@ INT8, UINT8, INT32, UINT32, INT64, UINT64, FLOAT16, FLOAT32, FLOAT64, BFLOAT16 =
 # b200c_redop_t (ncclRedOp_t numbering)
 SUM, PROD, MAX, MIN, AVG = range(5)
 # b200c_algo_t
-ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS, ALGO_NVLS_PIPE, ALGO_LL, ALGO_NVLS_LANES = range(7)
+ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS, ALGO_NVLS_PIPE, ALGO_LL, ALGO_NVLS_LANES, ALGO_NVLS_STREAMS = range(8)
 # b200c_share_mode_t
 SHARE_VMM_FD, SHARE_LEGACY_IPC = 0, 1
 MAX_RANKS = 8
@@ -45,7 +45,8 @@ class Config(Structure):
                 ("nvls_pipe_min_bytes", c_uint64), ("timeout_ms", c_uint64), ("granule_bytes", c_uint64),
                 ("ll_max_bytes", c_uint64), ("bcast_rounds_min_bytes", c_uint64), ("nvls_blocks", c_uint32),
                 ("nvls_lanes", c_uint32), ("lane_granule_bytes", c_uint64), ("nvls_lanes_min_bytes", c_uint64),
-                ("nvls_unroll", c_uint32), ("rounds_order", c_uint32)]
+                ("nvls_unroll", c_uint32), ("rounds_order", c_uint32), ("nvls_streams_min_bytes", c_uint64),
+                ("nvls_streams_piece_bytes", c_uint64)]
 
 
 class Props(Structure):

@@ -136,6 +136,8 @@ def make_config(**overrides):
         "B200COLL_NVLS_LANES_MIN_BYTES": ("nvls_lanes_min_bytes", int),
         "B200COLL_NVLS_UNROLL": ("nvls_unroll", int),
         "B200COLL_ROUNDS_ORDER": ("rounds_order", int),
+        "B200COLL_NVLS_STREAMS_MIN_BYTES": ("nvls_streams_min_bytes", int),
+        "B200COLL_NVLS_STREAMS_PIECE_BYTES": ("nvls_streams_piece_bytes", int),
         "B200COLL_TIMEOUT_MS": ("timeout_ms", int),
         "B200COLL_P2P_SLOT_BYTES": ("p2p_slot_bytes", int),
         "B200COLL_P2P_SLOTS": ("p2p_slots", int),

@@ -152,6 +152,9 @@ struct b200c_comm {
   uint32_t pipe_base = 0;  // flag epoch of the round-pipelined kernels (advanced by the round count of each op)
   uint32_t ll_seq = 0;     // LL op counter (flag value of the packed stores; region half = ll_seq & 1)
   int local_scale_ctas_per_sm = 0, tma_ctas_per_sm = 0;
+  // multi-stream NVLS pipeline: internal streams (copy-in, switch, copy-out) and per-region events
+  cudaStream_t ps_in = nullptr, ps_nv = nullptr, ps_out = nullptr;
+  cudaEvent_t pe_start = nullptr, pe_in[8] = {}, pe_nv[8] = {}, pe_out[8] = {};
   uint32_t send_cells[kMaxRanks] = {};
   uint32_t recv_cells[kMaxRanks] = {};
   uint32_t msend_cells = 0;            // multi-reader ring of this rank: cells sent so far
@@ -215,6 +218,8 @@ extern "C" void b200c_default_config(b200c_config_t* cfg) {
   cfg->ll_max_bytes = 64ull << 10;    // W=8: LL 12 us vs one-shot 13 us at 64 KiB, 15 vs 15 at 128 KiB (profiles/r02_sweep8_small.log)
   cfg->bcast_rounds_min_bytes = 4ull << 20;
   cfg->nvls_unroll = 4;
+  cfg->nvls_streams_min_bytes = 0;          // opt-in until measured on the target box
+  cfg->nvls_streams_piece_bytes = 128ull << 20;
   cfg->rounds_order = 0;
   cfg->nvls_lanes = 48;
   cfg->lane_granule_bytes = 64ull << 10;
@@ -305,6 +310,8 @@ extern "C" int b200c_comm_create(int rank, int world, int device, const b200c_co
   if (cfg.nvls_lanes > cfg.max_blocks / 2) cfg.nvls_lanes = cfg.max_blocks / 2 ? cfg.max_blocks / 2 : 1;
   if (cfg.lane_granule_bytes == 0) cfg.lane_granule_bytes = 64ull << 10;
   if (cfg.lane_granule_bytes % 8192) return fail(B200C_EINVAL, "lane_granule_bytes must be a multiple of 8 KiB");
+  if (cfg.nvls_streams_piece_bytes == 0) cfg.nvls_streams_piece_bytes = 128ull << 20;
+  if (cfg.nvls_streams_piece_bytes % (1u << 20)) return fail(B200C_EINVAL, "nvls_streams_piece_bytes must be a multiple of 1 MiB");
   // measured crossovers (profiles/r01_sweep_*): W=2 one-shot wins to 8 MiB; W=8 one-shot 23 us vs NVLS 28 us at 1 MiB
   if (cfg.oneshot_max_bytes == 0) cfg.oneshot_max_bytes = world <= 2 ? (8ull << 20) : (1ull << 20);
 
@@ -556,6 +563,8 @@ extern "C" int b200c_comm_destroy(b200c_comm_t* c) {
       else cudaIpcCloseMemHandle(c->arena[j]);
     }
   }
+  if (c->ps_in) { cudaStreamDestroy(c->ps_in); cudaStreamDestroy(c->ps_nv); cudaStreamDestroy(c->ps_out); cudaEventDestroy(c->pe_start);
+    for (int i = 0; i < 8; i++) { if (c->pe_in[i]) cudaEventDestroy(c->pe_in[i]); if (c->pe_nv[i]) cudaEventDestroy(c->pe_nv[i]); if (c->pe_out[i]) cudaEventDestroy(c->pe_out[i]); } }
   if (c->status_host) cudaFreeHost((void*)c->status_host);
   c->status_host = nullptr;
   cudaGetLastError();
@@ -765,6 +774,123 @@ static int local_scale_grid(b200c_comm* c, size_t bytes) {
   return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-stream staged NVLS (the largest plain tensors).  Instead of one kernel that interleaves local copies
+// with switch traffic, the message is cut into pieces and every piece runs three ordinary kernels on three
+// internal streams, chained by events:
+//     copy-in(i)  [user -> staging region i % R, any grid]      on ps_in
+//     switch(i)   [the 32-CTA zero-copy NVLS kernel on region]  on ps_nv   (the only kernel that waits for peers)
+//     copy-out(i) [region -> user]                              on ps_out
+// so copy-in(i+1) and copy-out(i-1) overlap switch(i), the switch kernel keeps its few CTAs streaming, and the
+// copies are plain full-speed local kernels that never spin.  A barrier op opens the pipeline (every peer has
+// finished what it did before, so both staging halves are free to serve as R regions) and another one closes it
+// on the caller's stream after the last copy-out (no later op of a peer can touch this rank's staging while a
+// copy-out still reads it).  Region reuse: copy-in(i+R) waits for copy-out(i); every peer finished reducing
+// region i before switch(i) completed (flag B).
+// ------------------------------------------------------------------------------------------------
+template <typename TS, typename TD, bool BYPASS>
+static void launch_stage_copy(const void* src, void* dst, size_t n, int sm_count, cudaStream_t s) {
+  size_t tile = kStageTileBytes / (sizeof(TS) > sizeof(TD) ? sizeof(TS) : sizeof(TD));
+  size_t want = (n + tile - 1) / tile, cap = (size_t)sm_count * 4;
+  int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  k_stage_copy<TS, TD, BYPASS><<<grid, kThreads, 0, s>>>(static_cast<const TS*>(src), static_cast<TD*>(dst), n);
+}
+static int pipeline_setup(b200c_comm* c) {
+  if (c->ps_in) return B200C_OK;
+  int lo = 0, hi = 0;
+  RT(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  RT(cudaStreamCreateWithPriority(&c->ps_in, cudaStreamNonBlocking, lo));
+  RT(cudaStreamCreateWithPriority(&c->ps_nv, cudaStreamNonBlocking, hi));   // the switch kernel's CTAs go first
+  RT(cudaStreamCreateWithPriority(&c->ps_out, cudaStreamNonBlocking, lo));
+  RT(cudaEventCreateWithFlags(&c->pe_start, cudaEventDisableTiming));
+  for (int i = 0; i < 8; i++) {
+    RT(cudaEventCreateWithFlags(&c->pe_in[i], cudaEventDisableTiming));
+    RT(cudaEventCreateWithFlags(&c->pe_nv[i], cudaEventDisableTiming));
+    RT(cudaEventCreateWithFlags(&c->pe_out[i], cudaEventDisableTiming));
+  }
+  return B200C_OK;
+}
+static int barrier_op(b200c_comm* c, cudaStream_t s) {
+  CollArgs a;
+  base_args(c, &a);
+  a.sig = make_sig(OPC_BARRIER, 0, 0, 0, -1, 0);
+  k_barrier<<<1, 32, 0, s>>>(a);
+  int rc = launch_check(c, "barrier");
+  if (rc) return rc;
+  commit_args(c, a);
+  return B200C_OK;
+}
+static int allreduce_streams(b200c_comm* c, const void* send, void* recv, size_t count, int dtype, int wire, int op, float scale,
+                             int has_scale, cudaStream_t user) {
+  (void)op;
+  const int W = c->world;
+  const size_t esz = b200c_dtype_size(dtype), wsz = b200c_dtype_size(wire), vec = 16 / wsz;
+  int rc = pipeline_setup(c);
+  if (rc) return rc;
+  size_t piece_bytes = c->cfg.nvls_streams_piece_bytes;
+  size_t area = 2 * c->cfg.staging_bytes;
+  while (area / piece_bytes < 3 && piece_bytes > (1u << 20)) piece_bytes /= 2;
+  int R = (int)(area / piece_bytes);
+  if (R < 3) return fail(B200C_EINVAL, "staging_bytes too small for the multi-stream pipeline");
+  if (R > 8) R = 8;
+  const size_t piece_elems = piece_bytes / wsz / (vec * W) * (vec * W);
+  const int P = (int)((count + piece_elems - 1) / piece_elems);
+  const uint32_t cap = c->cfg.nvls_blocks && c->cfg.nvls_blocks < c->cfg.max_blocks ? c->cfg.nvls_blocks : c->cfg.max_blocks;
+  // open: every peer has finished its previous op, so the whole staging area is ours to partition
+  rc = barrier_op(c, user);
+  if (rc) return rc;
+  RT(cudaEventRecord(c->pe_start, user));
+  RT(cudaStreamWaitEvent(c->ps_in, c->pe_start, 0));
+  for (int i = 0; i < P; i++) {
+    const int reg = i % R;
+    const size_t e0 = (size_t)i * piece_elems, n = count - e0 < piece_elems ? count - e0 : piece_elems;
+    char* region = c->arena[c->rank] + c->off_staging + (size_t)reg * piece_bytes;
+    const char* src = static_cast<const char*>(send) + e0 * esz;
+    char* dst = static_cast<char*>(recv) + e0 * esz;
+    if (i >= R) RT(cudaStreamWaitEvent(c->ps_in, c->pe_out[reg], 0));   // the region's previous piece has been copied out
+    if (wire == dtype) {
+      if (esz == 4) launch_stage_copy<float, float, false>(src, region, n, c->sm_count, c->ps_in);
+      else launch_stage_copy<bf16_t, bf16_t, false>(src, region, n, c->sm_count, c->ps_in);   // 2-byte payload: a plain copy either way
+    } else if (wire == B200C_BFLOAT16) launch_stage_copy<float, bf16_t, false>(src, region, n, c->sm_count, c->ps_in);
+    else launch_stage_copy<float, f16_t, false>(src, region, n, c->sm_count, c->ps_in);
+    rc = launch_check(c, "stage_in");
+    if (rc) return rc;
+    RT(cudaEventRecord(c->pe_in[reg], c->ps_in));
+    RT(cudaStreamWaitEvent(c->ps_nv, c->pe_in[reg], 0));
+    CollArgs a;
+    base_args(c, &a);
+    a.in = region; a.out = region;
+    a.has_scale = has_scale; a.scale = scale;
+    a.nvls_unroll = (int)c->cfg.nvls_unroll;
+    a.n = n;
+    a.chunk = round_up((n + W - 1) / W, vec);
+    a.symmetric = 1;
+    a.sym_off = (size_t)(region - c->arena[c->rank]);
+    int grid;
+    plan_tiles(a.chunk, wsz, vec, cap, kMinTileBytes, c->cfg.granule_bytes, &a.tile, &grid);
+    a.sig = make_sig(OPC_ALLREDUCE, dtype * 16 + wire, B200C_SUM, n, reg, B200C_ALGO_NVLS_STREAMS * 8 + i % 8);
+    if (wire == B200C_FLOAT32) launch_nvls<float, float>(a, grid, c->ps_nv, false);
+    else if (wire == B200C_BFLOAT16) launch_nvls<bf16_t, bf16_t>(a, grid, c->ps_nv, false);
+    else launch_nvls<f16_t, f16_t>(a, grid, c->ps_nv, false);
+    rc = launch_check(c, "nvls(stream pipeline)");
+    if (rc) return rc;
+    commit_args(c, a);
+    RT(cudaEventRecord(c->pe_nv[reg], c->ps_nv));
+    RT(cudaStreamWaitEvent(c->ps_out, c->pe_nv[reg], 0));
+    if (wire == dtype) {
+      if (esz == 4) launch_stage_copy<float, float, true>(region, dst, n, c->sm_count, c->ps_out);
+      else launch_stage_copy<bf16_t, bf16_t, true>(region, dst, n, c->sm_count, c->ps_out);
+    } else if (wire == B200C_BFLOAT16) launch_stage_copy<bf16_t, float, true>(region, dst, n, c->sm_count, c->ps_out);
+    else launch_stage_copy<f16_t, float, true>(region, dst, n, c->sm_count, c->ps_out);
+    rc = launch_check(c, "stage_out");
+    if (rc) return rc;
+    RT(cudaEventRecord(c->pe_out[reg], c->ps_out));
+  }
+  // close: the caller's stream continues after the last copy-out, and peers only move on after this rank got here
+  RT(cudaStreamWaitEvent(user, c->pe_out[(P - 1) % R], 0));
+  return barrier_op(c, user);
+}
+
 static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t count, int dtype, int wire, int op, float scale,
                           int has_scale, int algo, cudaStream_t s) {
   int rc = check_ready(c);
@@ -777,7 +903,7 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     if (!(dtype == B200C_FLOAT32 && (wire == B200C_BFLOAT16 || wire == B200C_FLOAT16))) return fail(B200C_EUNSUPPORTED, "wire dtype %d for buffer dtype %d", wire, dtype);
     if (op != B200C_SUM && op != B200C_AVG) return fail(B200C_EUNSUPPORTED, "compressed wire supports SUM/AVG only");
   }
-  if (algo < B200C_ALGO_AUTO || algo > B200C_ALGO_NVLS_LANES) return fail(B200C_EINVAL, "bad algo %d", algo);
+  if (algo < B200C_ALGO_AUTO || algo > B200C_ALGO_NVLS_STREAMS) return fail(B200C_EINVAL, "bad algo %d", algo);
   if (op == B200C_AVG) { has_scale = 1; scale = 1.f / (float)c->world; }
   if (count == 0) return B200C_OK;
   DeviceGuard g(c->device);
@@ -806,11 +932,10 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_local_scale_tma<float, bf16_t>, kTmaThreads, kTmaSmemBytes) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
         c->tma_ctas_per_sm = nb;
       }
-      // balanced persistent grid: every CTA gets the same number of tiles (1920 tiles on 444 resident CTAs would
-      // leave most CTAs idle while a few run a fifth tile: 384 CTAs x 5 tiles instead)
+      // as many CTAs as are resident at once (measured: a smaller "balanced" grid of 384 x 5 tiles is slower, 13.7 vs
+      // 12.9 us per 30 MiB bucket — what counts is how many bulk loads are in flight from the first microsecond)
       size_t cap = (size_t)c->sm_count * c->tma_ctas_per_sm;
-      size_t per_cta = (ntiles + cap - 1) / cap;
-      int tgrid = (int)((ntiles + per_cta - 1) / per_cta);
+      int tgrid = (int)(ntiles < cap ? ntiles : cap);
       switch (dtype * 16 + wire) {
         case B200C_FLOAT32 * 16 + B200C_FLOAT32: k_local_scale_tma<float, float><<<tgrid, kTmaThreads, kTmaSmemBytes, s>>>(a); break;
         case B200C_FLOAT32 * 16 + B200C_BFLOAT16: k_local_scale_tma<float, bf16_t><<<tgrid, kTmaThreads, kTmaSmemBytes, s>>>(a); break;
@@ -843,7 +968,7 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
 
   const bool nvls_ok = c->mc_arena && (op == B200C_SUM || op == B200C_AVG) &&
                        (wire == B200C_FLOAT32 || wire == B200C_BFLOAT16 || wire == B200C_FLOAT16);
-  if ((algo == B200C_ALGO_NVLS || algo == B200C_ALGO_NVLS_PIPE || algo == B200C_ALGO_NVLS_LANES) && !nvls_ok) return fail(B200C_EUNSUPPORTED, "NVLS needs a bound multicast object, SUM/AVG and f32/bf16/f16");
+  if ((algo == B200C_ALGO_NVLS || algo == B200C_ALGO_NVLS_PIPE || algo == B200C_ALGO_NVLS_LANES || algo == B200C_ALGO_NVLS_STREAMS) && !nvls_ok) return fail(B200C_EUNSUPPORTED, "NVLS needs a bound multicast object, SUM/AVG and f32/bf16/f16");
   const bool ll_ok = wire == dtype && c->ll_words && count * esz <= c->ll_words * 4;
   if (algo == B200C_ALGO_LL && !ll_ok) return fail(B200C_EUNSUPPORTED, "LL needs wire == dtype and at most %zu bytes (ll_max_bytes)", c->ll_words * 4);
   // the zero-copy kernel is pure switch traffic (few CTAs are best); the staged kernels also do the local copies
@@ -856,6 +981,9 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     const char* base = c->arena[c->rank] + c->off_sym;
     in_sym = in >= base && in + count * esz <= base + c->sym_bytes;
   }
+  if (!in_sym && (algo == B200C_ALGO_NVLS_STREAMS ||
+                  (algo == B200C_ALGO_AUTO && nvls_ok && W >= 6 && c->cfg.nvls_streams_min_bytes && count * wsz >= c->cfg.nvls_streams_min_bytes)))
+    return allreduce_streams(c, send, recv, count, dtype, wire, op, scale, has_scale, s);
   size_t done = 0;
   while (done < count) {
     size_t left = count - done;

@@ -612,6 +612,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_allreduce_nvls_lanes(const __gr
   }
 }
 
+// Plain local staging copy (user tensor <-> arena region), one CTA per tile, grid-stride.  Used by the
+// multi-stream NVLS pipeline, where copies and switch traffic are separate kernels on separate streams.
+// BYPASS: the source was written by remote multimem stores (read past L1).
+constexpr size_t kStageTileBytes = 32768;
+template <typename TS, typename TD, bool BYPASS>
+__global__ void __launch_bounds__(kThreads) k_stage_copy(const TS* __restrict__ src, TD* __restrict__ dst, size_t n) {
+  constexpr size_t T = kStageTileBytes / (sizeof(TS) > sizeof(TD) ? sizeof(TS) : sizeof(TD));
+  for (size_t t0 = (size_t)blockIdx.x * T; t0 < n; t0 += (size_t)gridDim.x * T)
+    move_tile<TS, TD, BYPASS>(dst + t0, src + t0, n - t0 < T ? n - t0 : T);
+}
+
 // world == 1: no peers, only the wire rounding and the scale remain (the DDP hook at N = 1).
 // Grid-stride over 16-byte vectors, four loads in flight per thread; the host sizes the grid to the
 // resident capacity (no second, partial wave); HBM-bound (read n, write n).

@@ -64,7 +64,8 @@ typedef enum {
   B200C_ALGO_NVLS = 3,    /* multimem.ld_reduce / multimem.st on the NVSwitch multicast object */
   B200C_ALGO_NVLS_PIPE = 4,/* same, staged copies overlapped with the switch traffic (per-round flags, software-pipelined blocks) */
   B200C_ALGO_LL = 5,       /* packed {data, flag} 8-byte stores, one NVLink hop, no fence: small messages */
-  B200C_ALGO_NVLS_LANES = 6 /* staged NVLS in lanes: few switch-only CTAs + many copy-only CTAs over an L2-resident staging ring */
+  B200C_ALGO_NVLS_LANES = 6,/* staged NVLS in lanes: few switch-only CTAs + many copy-only CTAs over an L2-resident staging ring */
+  B200C_ALGO_NVLS_STREAMS = 7 /* staged NVLS as a pipeline of kernels on internal streams: copy-in | 32-CTA zero-copy NVLS | copy-out per piece */
 } b200c_algo_t;
 
 typedef enum {
@@ -106,6 +107,8 @@ typedef struct {
   uint64_t nvls_lanes_min_bytes; /* AUTO: staged NVLS messages >= this use the lane kernel (0 = never) */
   uint32_t nvls_unroll;        /* multimem.ld_reduce vectors in flight per thread: 4 or 8 */
   uint32_t rounds_order;       /* round-pipelined kernel: 1 = copy round q-1 out before the switch stage of round q */
+  uint64_t nvls_streams_min_bytes; /* AUTO: staged NVLS messages >= this use the multi-stream pipeline (0 = never) */
+  uint64_t nvls_streams_piece_bytes; /* bytes (on the wire) per pipeline piece; at least 3 pieces must fit 2 * staging_bytes */
 } b200c_config_t;
 
 typedef struct {

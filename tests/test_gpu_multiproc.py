@@ -203,6 +203,18 @@ class RawWorker:
         self.comm.check()
         return x.cpu()
 
+    def streams_then_twoshot(self, n):
+        """No host synchronisation between the pipeline and the next staged op."""
+        from ant_ray_b200 import _native as N
+
+        x = make_input(torch.float32, n, self.rank).cuda()
+        y = make_input(torch.int32, 100_003, self.rank).cuda()
+        self.comm.allreduce(x.data_ptr(), x.data_ptr(), n, N.FLOAT32, N.SUM, N.ALGO_NVLS_STREAMS)
+        self.comm.allreduce(y.data_ptr(), y.data_ptr(), 100_003, N.INT32, N.SUM, N.ALGO_TWOSHOT)
+        torch.cuda.synchronize()
+        self.comm.check()
+        return x.cpu(), y.cpu()
+
     def pool_allreduce(self, n):
         """Ordinary torch tensors from the communicator's MemPool are zero-copy: NVLS reduces them in place."""
         from ant_ray_b200 import _native as N
@@ -311,7 +323,8 @@ def test_nvls_allreduce(raw_world, dtype):
     if not all(get([a.has_multicast.remote() for a in actors])):
         pytest.skip("multicast object not bound on this box")
     for n in (16, 100_003, 3_000_001):
-        for symmetric, algo in ((False, N.ALGO_NVLS), (True, N.ALGO_NVLS), (False, N.ALGO_NVLS_PIPE), (False, N.ALGO_NVLS_LANES)):
+        for symmetric, algo in ((False, N.ALGO_NVLS), (True, N.ALGO_NVLS), (False, N.ALGO_NVLS_PIPE), (False, N.ALGO_NVLS_LANES),
+                                (False, N.ALGO_NVLS_STREAMS)):
             if symmetric and (n * torch.empty((), dtype=dtype).element_size()) % 16:
                 continue
             outs = get([a.allreduce.remote(dtype, n, N.SUM, algo, None, symmetric) for a in actors])
@@ -354,20 +367,28 @@ def test_nvls_pipelined_multi_piece_and_fused(raw_world):
     assert torch.allclose(outs[0], want, rtol=1e-5, atol=4e-5)
     for r in range(1, W):
         assert_equal_bits(outs[r], outs[0], "every rank must hold identical bits")
-    for algo in (N.ALGO_NVLS_PIPE, N.ALGO_NVLS_LANES):
+    for algo in (N.ALGO_NVLS_PIPE, N.ALGO_NVLS_LANES, N.ALGO_NVLS_STREAMS):
         outs = get([a.allreduce.remote(torch.float32, n, N.SUM, algo, torch.bfloat16) for a in actors])
         want = O.allreduce_scaled([make_input(torch.float32, n, r) for r in range(W)], torch.bfloat16, 1.0 / W)
         assert torch.allclose(outs[0], want, rtol=2e-2, atol=2e-2)
         for r in range(1, W):
             assert_equal_bits(outs[r], outs[0], "every rank must hold identical bits")
-    # lane kernel: one launch for a message several times the staging half (8 MiB here), many ring rounds, 20 in a row
+    # lane kernel: one launch for a message several times the staging half (8 MiB here), many ring rounds, 20 in a row;
+    # multi-stream pipeline: 9 pieces of 4 MiB through 4 staging regions (region reuse), 10 in a row, then a staged
+    # op of another kind right behind it (the closing barrier must keep its staging writes away from the last copy-out)
     n = 9_000_017
-    for _ in range(20):
-        outs = get([a.allreduce.remote(torch.float32, n, N.SUM, N.ALGO_NVLS_LANES) for a in actors])
     want = O.allreduce([make_input(torch.float32, n, r) for r in range(W)])
-    assert torch.allclose(outs[0], want, rtol=1e-5, atol=4e-5)
-    for r in range(1, W):
-        assert_equal_bits(outs[r], outs[0], "every rank must hold identical bits")
+    for algo, reps in ((N.ALGO_NVLS_LANES, 20), (N.ALGO_NVLS_STREAMS, 10)):
+        for _ in range(reps):
+            outs = get([a.allreduce.remote(torch.float32, n, N.SUM, algo) for a in actors])
+        assert torch.allclose(outs[0], want, rtol=1e-5, atol=4e-5)
+        for r in range(1, W):
+            assert_equal_bits(outs[r], outs[0], "every rank must hold identical bits")
+    outs = get([a.streams_then_twoshot.remote(n) for a in actors])
+    want_i = O.allreduce([make_input(torch.int32, 100_003, r) for r in range(W)])
+    for r in range(W):
+        assert torch.allclose(outs[r][0], want, rtol=1e-5, atol=4e-5)
+        assert_equal_bits(outs[r][1], want_i, "two-shot right behind the pipeline")
 
 
 def test_broadcast_all_gpus(raw_world):

@@ -92,7 +92,7 @@ def main():
         if algo_name == "nvls_sym":
             over["symmetric_bytes"] = max(sizes)
         variants.append((label, algo_name, PeerMemoryComm(world, rank, f"sweep-var-{label}", local, None, make_config(**over))))
-    algos = {"auto": N.ALGO_AUTO, "ll": N.ALGO_LL, "nvls_lanes": N.ALGO_NVLS_LANES, "oneshot": N.ALGO_ONESHOT, "twoshot": N.ALGO_TWOSHOT, "nvls": N.ALGO_NVLS, "nvls_sym": N.ALGO_NVLS,
+    algos = {"auto": N.ALGO_AUTO, "ll": N.ALGO_LL, "nvls_lanes": N.ALGO_NVLS_LANES, "nvls_streams": N.ALGO_NVLS_STREAMS, "oneshot": N.ALGO_ONESHOT, "twoshot": N.ALGO_TWOSHOT, "nvls": N.ALGO_NVLS, "nvls_sym": N.ALGO_NVLS,
              "nvls_pipe": N.ALGO_NVLS_PIPE}
     out = {"world": world, "dtype": a.dtype, "multicast": bool(comm.multicast), "nccl_version": ".".join(map(str, torch.cuda.nccl.version())),
            "max_blocks": comm.config.max_blocks, "rows": []}
