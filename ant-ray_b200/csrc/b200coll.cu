@@ -218,7 +218,7 @@ extern "C" void b200c_default_config(b200c_config_t* cfg) {
   cfg->ll_max_bytes = 64ull << 10;    // W=8: LL 12 us vs one-shot 13 us at 64 KiB, 15 vs 15 at 128 KiB (profiles/r02_sweep8_small.log)
   cfg->bcast_rounds_min_bytes = 4ull << 20;
   cfg->nvls_unroll = 4;
-  cfg->nvls_streams_min_bytes = 0;          // opt-in until measured on the target box
+  cfg->nvls_streams_min_bytes = 768ull << 20;   // W=8, 1 GiB: 737 GB/s vs 704 (rounds kernel) and NCCL 726; 512 MiB: a tie (r02_sweep8_streams.log)
   cfg->nvls_streams_piece_bytes = 128ull << 20;
   cfg->rounds_order = 0;
   cfg->nvls_lanes = 48;
@@ -834,16 +834,30 @@ static int allreduce_streams(b200c_comm* c, const void* send, void* recv, size_t
   if (R < 3) return fail(B200C_EINVAL, "staging_bytes too small for the multi-stream pipeline");
   if (R > 8) R = 8;
   const size_t piece_elems = piece_bytes / wsz / (vec * W) * (vec * W);
-  const int P = (int)((count + piece_elems - 1) / piece_elems);
+  // Piece sizes: the pipeline's fill (first copy-in) and drain (last copy-out) are not overlapped with anything, so
+  // the first and the last piece are a quarter of the regular size.
+  const size_t small = piece_elems / 4 / (vec * W) * (vec * W);
   const uint32_t cap = c->cfg.nvls_blocks && c->cfg.nvls_blocks < c->cfg.max_blocks ? c->cfg.nvls_blocks : c->cfg.max_blocks;
   // open: every peer has finished its previous op, so the whole staging area is ours to partition
   rc = barrier_op(c, user);
   if (rc) return rc;
   RT(cudaEventRecord(c->pe_start, user));
   RT(cudaStreamWaitEvent(c->ps_in, c->pe_start, 0));
-  for (int i = 0; i < P; i++) {
+  size_t e0 = 0;
+  int last_reg = 0;
+  for (int i = 0; e0 < count; i++) {
     const int reg = i % R;
-    const size_t e0 = (size_t)i * piece_elems, n = count - e0 < piece_elems ? count - e0 : piece_elems;
+    last_reg = reg;
+    const size_t left = count - e0;
+    size_t n;
+    if (small && count > 2 * piece_elems) {
+      if (i == 0) n = small;
+      else if (left <= small) n = left;
+      else if (left <= piece_elems + small) n = left - small;   // the piece before the short last one takes the remainder
+      else n = piece_elems;
+    } else {
+      n = left < piece_elems ? left : piece_elems;
+    }
     char* region = c->arena[c->rank] + c->off_staging + (size_t)reg * piece_bytes;
     const char* src = static_cast<const char*>(send) + e0 * esz;
     char* dst = static_cast<char*>(recv) + e0 * esz;
@@ -885,9 +899,10 @@ static int allreduce_streams(b200c_comm* c, const void* send, void* recv, size_t
     rc = launch_check(c, "stage_out");
     if (rc) return rc;
     RT(cudaEventRecord(c->pe_out[reg], c->ps_out));
+    e0 += n;
   }
   // close: the caller's stream continues after the last copy-out, and peers only move on after this rank got here
-  RT(cudaStreamWaitEvent(user, c->pe_out[(P - 1) % R], 0));
+  RT(cudaStreamWaitEvent(user, c->pe_out[last_reg], 0));
   return barrier_op(c, user);
 }
 

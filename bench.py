@@ -564,6 +564,7 @@ def run_parity(comm, dist, world, rank, device, wire):
         check_allreduce("nvls_rounds", N.ALGO_NVLS_PIPE, (16 << 20) + 4, use_int=False)
         check_allreduce("nvls_lanes", N.ALGO_NVLS_LANES, (24 << 20) + 12, use_int=False)
         check_allreduce("nvls_streams", N.ALGO_NVLS_STREAMS, (40 << 20) + 12, use_int=False)
+        check_allreduce("auto_1GiB", N.ALGO_AUTO, 256 << 20)   # W >= 6: the multi-stream pipeline with ramped piece sizes
         check_allreduce("nvls_symmetric", N.ALGO_NVLS, 4 << 20, use_int=False, sym=True)
     # fused gradient mean, 16-bit wire: against the reference's own formulation (bf16_compress_hook:
     # buffer.to(bf16).div_(W) -> allreduce -> copy back, torch default_hooks.py)
