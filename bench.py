@@ -715,13 +715,17 @@ def run_comm_bound(args, dist, world, device, steps=30, warmup=8):
         step = make_step(model, opt, True, device)
         for _ in range(warmup):
             step(x, y)
-        state.time_kernels, state.events = True, []
+        # this step is bound by the host's launch rate, so the per-bucket event pair of `time_kernels` would be on the
+        # critical path: throughput is timed without it, the hook's device time in a short second pass
         ms, _ = timed_steps(step, x, y, steps, dist, world)
+        state.time_kernels, state.events = True, []
+        ksteps = max(4, steps // 4)
+        timed_steps(step, x, y, ksteps, dist, world)
         kt = state.kernel_times_ms()
         state.time_kernels = False
         row["b200_images_per_sec"] = round(world * B * steps / (ms / 1e3), 1)
         row["b200_ms_per_step"] = round(ms / steps, 3)
-        row["b200_hook_ms_per_step"] = round(sum(t for t, _ in kt) / steps, 4)
+        row["b200_hook_ms_per_step"] = round(sum(t for t, _ in kt) / ksteps, 4)
         state.comm.destroy()
         del model, opt, step
         m2 = DistributedDataParallel(build_model(device), device_ids=[device], output_device=device)
