@@ -134,8 +134,6 @@ def make_config(**overrides):
         "B200COLL_NVLS_LANES": ("nvls_lanes", int),
         "B200COLL_LANE_GRANULE_BYTES": ("lane_granule_bytes", int),
         "B200COLL_NVLS_LANES_MIN_BYTES": ("nvls_lanes_min_bytes", int),
-        "B200COLL_NVLS_UNROLL": ("nvls_unroll", int),
-        "B200COLL_ROUNDS_ORDER": ("rounds_order", int),
         "B200COLL_NVLS_STREAMS_MIN_BYTES": ("nvls_streams_min_bytes", int),
         "B200COLL_NVLS_STREAMS_PIECE_BYTES": ("nvls_streams_piece_bytes", int),
         "B200COLL_TIMEOUT_MS": ("timeout_ms", int),

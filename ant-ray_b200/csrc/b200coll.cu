@@ -750,10 +750,19 @@ enum { OPC_ALLREDUCE = 1, OPC_REDUCE, OPC_BROADCAST, OPC_ALLGATHER, OPC_REDUCESC
 constexpr size_t kMinTileBytes = 8192;
 
 // mixed-type (bucket dtype != wire dtype) and NVLS launches live in this TU
+template <typename TI, typename TW, int WT>
+static void launch_mixed_w(int algo, const CollArgs& a, int grid, cudaStream_t s) {
+  if (algo == B200C_ALGO_ONESHOT) k_allreduce_oneshot<TI, TW, B200C_SUM, WT><<<grid, kThreads, 0, s>>>(a);
+  else k_allreduce_twoshot<TI, TW, B200C_SUM, WT><<<grid, kThreads, 0, s>>>(a);
+}
 template <typename TI, typename TW>
 static void launch_mixed(int algo, const CollArgs& a, int grid, cudaStream_t s) {
-  if (algo == B200C_ALGO_ONESHOT) k_allreduce_oneshot<TI, TW, B200C_SUM><<<grid, kThreads, 0, s>>>(a);
-  else k_allreduce_twoshot<TI, TW, B200C_SUM><<<grid, kThreads, 0, s>>>(a);
+  switch (a.c.world) {
+    case 2: launch_mixed_w<TI, TW, 2>(algo, a, grid, s); break;
+    case 4: launch_mixed_w<TI, TW, 4>(algo, a, grid, s); break;
+    case 8: launch_mixed_w<TI, TW, 8>(algo, a, grid, s); break;
+    default: launch_mixed_w<TI, TW, 0>(algo, a, grid, s); break;
+  }
 }
 template <typename TI, typename TW>
 static void launch_nvls(const CollArgs& a, int grid, cudaStream_t s, bool pipe, bool lanes = false) {
@@ -875,7 +884,6 @@ static int allreduce_streams(b200c_comm* c, const void* send, void* recv, size_t
     base_args(c, &a);
     a.in = region; a.out = region;
     a.has_scale = has_scale; a.scale = scale;
-    a.nvls_unroll = (int)c->cfg.nvls_unroll;
     a.n = n;
     a.chunk = round_up((n + W - 1) / W, vec);
     a.symmetric = 1;
@@ -1017,7 +1025,6 @@ static int allreduce_impl(b200c_comm* c, const void* send, void* recv, size_t co
     base_args(c, &a);
     a.in = in + done * esz; a.out = out + done * esz;
     a.has_scale = has_scale; a.scale = scale;
-    a.nvls_unroll = (int)c->cfg.nvls_unroll; a.rounds_order = (int)c->cfg.rounds_order;
     size_t n;
     int grid;
     uint32_t rounds = 0;

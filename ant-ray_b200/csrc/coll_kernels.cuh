@@ -32,11 +32,14 @@ __device__ __forceinline__ size_t clip_count(size_t lo, size_t hi, size_t n) {
        g0 < (extent);                                                                                          \
        g0 += (size_t)gridDim.x * (a).tile, g1 = g0 + (a).tile < (extent) ? g0 + (a).tile : (extent))
 
+// The reducing kernels are compiled once per world size (WT = 2, 4, 8; WT = 0 takes the world size at run time for
+// 3, 5, 6, 7): with the four reduce loops in one kernel the register allocator spilled loop invariants into local
+// memory under the 64-register budget; one loop per kernel compiles without a stack (profiles/*_sass_local_memory.txt).
 // ---------------------------------------------------------------------------------------------
 // one-shot allreduce: push the whole buffer to every peer, reduce locally.  One flag round.
 // staging slot s (n_pad elements of TW) on rank j holds rank s's data.
 // ---------------------------------------------------------------------------------------------
-template <typename TI, typename TW, int OP>
+template <typename TI, typename TW, int OP, int WT>
 __global__ void __launch_bounds__(kThreads, 2) k_allreduce_oneshot(const __grid_constant__ CollArgs a) {
   const DevComm& c = a.c;
   const int r = c.rank, W = c.world;
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_allreduce_oneshot(const __grid_
   if (!block_wait_all(my_flags(kOffFlagA, c), a.seq, c, 1)) return;
   check_signature(a);
   B200C_FOR_GRANULES(t0, t1, a, a.n) {
-    reduce_tile<TI, TW, OP>(a, staging_ptr<TW>(c, r, a.seq, 0) + t0, a.chunk, r, in + t0, nullptr, out + t0, t1 - t0);
+    reduce_tile<TI, TW, OP, WT>(a, staging_ptr<TW>(c, r, a.seq, 0) + t0, a.chunk, r, in + t0, nullptr, out + t0, t1 - t0);
   }
 }
 
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(kLLThreads) k_allreduce_ll(const __grid_consta
 //   B: reduce the W contributions of the own chunk in rank order; result -> own slot [r] + out
 //   C: pull every other rank's reduced granule                       (NVLink ingress, loads)
 // ---------------------------------------------------------------------------------------------
-template <typename TI, typename TW, int OP>
+template <typename TI, typename TW, int OP, int WT>
 __global__ void __launch_bounds__(kThreads, 2) k_allreduce_twoshot(const __grid_constant__ CollArgs a) {
   const DevComm& c = a.c;
   const int r = c.rank, W = c.world;
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_allreduce_twoshot(const __grid_
     size_t lo = (size_t)r * a.chunk + t0;
     size_t cnt = clip_count(lo, (size_t)r * a.chunk + t1, a.n);
     if (cnt)
-      reduce_tile<TI, TW, OP>(a, staging_ptr<TW>(c, r, a.seq, 0) + t0, a.chunk, r, in + lo, staging_ptr<TW>(c, r, a.seq, (size_t)r * slot_bytes) + t0, out + lo, cnt);
+      reduce_tile<TI, TW, OP, WT>(a, staging_ptr<TW>(c, r, a.seq, 0) + t0, a.chunk, r, in + lo, staging_ptr<TW>(c, r, a.seq, (size_t)r * slot_bytes) + t0, out + lo, cnt);
   }
   block_signal_all(kOffFlagB, a.seq, c);
   if (!block_wait_all(my_flags(kOffFlagB, c), a.seq, c, 2)) return;
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_allreduce_twoshot(const __grid_
 // reduce (root): every non-root pushes to root; root folds; root then releases the others.
 // Both are phases A+B of two-shot with full-size chunks.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int OP>
+template <typename T, int OP, int WT>
 __global__ void __launch_bounds__(kThreads, 2) k_reducescatter(const __grid_constant__ CollArgs a) {
   const DevComm& c = a.c;
   const int r = c.rank, W = c.world;
@@ -274,11 +277,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_reducescatter(const __grid_cons
   if (!block_wait_all(my_flags(kOffFlagA, c), a.seq, c, 1)) return;
   check_signature(a);
   B200C_FOR_GRANULES(t0, t1, a, a.n) {
-    reduce_tile<T, T, OP>(a, staging_ptr<T>(c, r, a.seq, 0) + t0, a.chunk, r, static_cast<const T*>(a.in_ptrs[r]) + t0, nullptr, static_cast<T*>(a.out) + t0, t1 - t0);
+    reduce_tile<T, T, OP, WT>(a, staging_ptr<T>(c, r, a.seq, 0) + t0, a.chunk, r, static_cast<const T*>(a.in_ptrs[r]) + t0, nullptr, static_cast<T*>(a.out) + t0, t1 - t0);
   }
 }
 
-template <typename T, int OP>
+template <typename T, int OP, int WT>
 __global__ void __launch_bounds__(kThreads, 2) k_reduce(const __grid_constant__ CollArgs a) {
   const DevComm& c = a.c;
   const int r = c.rank, root = a.root;
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_reduce(const __grid_constant__ 
     if (!block_wait_all(my_flags(kOffFlagA, c), a.seq, c, 1)) return;
     check_signature(a);
     B200C_FOR_GRANULES(t0, t1, a, a.n) {
-      reduce_tile<T, T, OP>(a, staging_ptr<T>(c, r, a.seq, 0) + t0, a.chunk, r, static_cast<const T*>(a.in) + t0, nullptr, static_cast<T*>(a.out) + t0, t1 - t0);
+      reduce_tile<T, T, OP, WT>(a, staging_ptr<T>(c, r, a.seq, 0) + t0, a.chunk, r, static_cast<const T*>(a.in) + t0, nullptr, static_cast<T*>(a.out) + t0, t1 - t0);
     }
     block_signal_all(kOffFlagB, a.seq, c);
   }
@@ -337,8 +340,9 @@ __device__ __forceinline__ void multimem_st16(void* p, uint4 v) {
 }
 
 // in-switch reduce of nv 16-byte vectors at multicast address `mc`, broadcast back in place.
-// U vectors are in flight per thread (a.nvls_unroll: 4 or 8): the staged kernels visit the switch in short
-// bursts between local copies, so each burst has to carry more bytes to keep the switch fed.
+// U = 4 vectors are in flight per thread.  (Eight were tried for the staged kernels, whose bursts between local copies
+// are short: 705-708 GB/s against 705 at 1 GiB, W=8 - profiles/r02_sweep8_unroll_order.log - and the second code path
+// cost the rounds kernel its spill-free register allocation, so it was removed.)
 template <typename TW, int U>
 __device__ __forceinline__ void nvls_reduce_bcast_u(char* mc, size_t nv, const CollArgs& a, size_t i) {
   constexpr int V = 16 / sizeof(TW);
@@ -370,8 +374,7 @@ __device__ __forceinline__ void nvls_reduce_bcast_u(char* mc, size_t nv, const C
 }
 template <typename TW>
 __device__ __forceinline__ void nvls_reduce_bcast(char* mc, size_t nv, const CollArgs& a) {
-  if (a.nvls_unroll >= 8) nvls_reduce_bcast_u<TW, 8>(mc, nv, a, threadIdx.x);
-  else nvls_reduce_bcast_u<TW, kUnroll>(mc, nv, a, threadIdx.x);
+  nvls_reduce_bcast_u<TW, kUnroll>(mc, nv, a, threadIdx.x);
 }
 // user tensor -> staging for the granule [g0, g1) of every rank chunk (zero-pad the last vector so the
 // switch reduces defined values)
@@ -486,10 +489,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_allreduce_nvls_rounds(const __g
       nvls_stage_in<TI, TW>(a, mine, in, lo_of(q + 1), hi_of(q + 1));
       round_signal(kOffPipeA, a.pipe_base + q + 2, c);
     }
-    if (a.rounds_order && q >= 1) {   // variant: copy round q-1 out BEFORE visiting the switch for round q
-      if (!round_wait(kOffPipeB, a.pipe_base + q, c, 2)) return;
-      nvls_stage_out<TI, TW>(a, mine, out, lo_of(q - 1), hi_of(q - 1));
-    }
     if (!round_wait(kOffPipeA, a.pipe_base + q + 1, c, 1)) return;
     {
       size_t lo = (size_t)r * a.chunk + lo_of(q);
@@ -497,7 +496,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_allreduce_nvls_rounds(const __g
       if (cnt) nvls_reduce_bcast<TW>(c.mc_arena + base_off + lo * sizeof(TW), (cnt + V - 1) / V, a);
     }
     round_signal(kOffPipeB, a.pipe_base + q + 1, c);
-    if (!a.rounds_order && q >= 1) {
+    if (q >= 1) {
       if (!round_wait(kOffPipeB, a.pipe_base + q, c, 2)) return;
       nvls_stage_out<TI, TW>(a, mine, out, lo_of(q - 1), hi_of(q - 1));
     }

@@ -86,8 +86,6 @@ struct CollArgs {
   uint32_t pipe_base;  // round-pipelined kernels: flag value of round q is pipe_base + q + 1
   uint32_t ll_seq;     // LL kernels: per-communicator LL op counter (flag value; half = ll_seq & 1)
   int lane_copy;       // lane kernel: copy CTAs per lane (each lane = 1 switch CTA + lane_copy copy CTAs)
-  int nvls_unroll;     // multimem vectors in flight per thread (4 or 8)
-  int rounds_order;    // rounds kernel: 1 = copy round q-1 out before the switch stage of round q
   int symmetric;   // NVLS: in/out already live at the same offset of the symmetric region
   size_t sym_off;  // arena offset of that buffer
   const void* in_ptrs[kMaxRanks];
@@ -322,6 +320,9 @@ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_c
 // tile primitives: the whole block cooperates on `n` contiguous elements.
 // ---------------------------------------------------------------------------------------------
 constexpr int kUnroll = 4;
+#ifndef B200C_CONVERT_UNROLL
+#define B200C_CONVERT_UNROLL 1   // converting copies (float bucket <-> 16-bit wire): vector steps in flight per thread
+#endif
 
 // Plain byte copy of n elements of T.  SRC_BYPASS: source is staging / peer memory.
 // `t` / `nt`: index of the calling thread within, and size of, the group of threads that cooperates
@@ -358,27 +359,45 @@ __device__ __forceinline__ void convert_tile(TD* __restrict__ dst, const TS* __r
   constexpr int V = VS > VD ? VS : VD;
   if (aligned16(dst) && aligned16(src)) {
     size_t nv = n / V;
-    for (size_t i = t; i < nv; i += nt) {
-      TS sv[V];
+    constexpr int NS = V / VS, ND = V / VD;   // 16-byte loads / stores per vector step
+    constexpr int U = B200C_CONVERT_UNROLL;   // vector steps in flight per thread
+    auto convert_store = [&](const uint4* raw, size_t i) {
       TD dv[V];
-      const uint4* s = reinterpret_cast<const uint4*>(src + i * V);
 #pragma unroll
-      for (int q = 0; q < V / VS; q++) {
+      for (int q = 0; q < NS; q++) {
         Pack16<TS> p;
-        p.u = SRC_BYPASS ? ld_bypass16(s + q) : s[q];
+        p.u = raw[q];
 #pragma unroll
-        for (int e = 0; e < VS; e++) sv[q * VS + e] = p.e[e];
+        for (int e = 0; e < VS; e++) dv[q * VS + e] = Traits<TD>::from_acc((typename Traits<TD>::A)Traits<TS>::to_acc(p.e[e]));
       }
-#pragma unroll
-      for (int e = 0; e < V; e++) dv[e] = Traits<TD>::from_acc((typename Traits<TD>::A)Traits<TS>::to_acc(sv[e]));
       uint4* d = reinterpret_cast<uint4*>(dst + i * V);
 #pragma unroll
-      for (int q = 0; q < V / VD; q++) {
+      for (int q = 0; q < ND; q++) {
         Pack16<TD> p;
 #pragma unroll
         for (int e = 0; e < VD; e++) p.e[e] = dv[q * VD + e];
         d[q] = p.u;
       }
+    };
+    size_t i = t;
+    if constexpr (U > 1)
+    for (; i + (size_t)(U - 1) * nt < nv; i += (size_t)U * nt) {
+      uint4 raw[U][NS];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint4* s = reinterpret_cast<const uint4*>(src + (i + (size_t)u * nt) * V);
+#pragma unroll
+        for (int q = 0; q < NS; q++) raw[u][q] = SRC_BYPASS ? ld_bypass16(s + q) : s[q];
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) convert_store(raw[u], i + (size_t)u * nt);
+    }
+    for (; i < nv; i += nt) {
+      uint4 raw[NS];
+      const uint4* s = reinterpret_cast<const uint4*>(src + i * V);
+#pragma unroll
+      for (int q = 0; q < NS; q++) raw[q] = SRC_BYPASS ? ld_bypass16(s + q) : s[q];
+      convert_store(raw, i);
     }
     for (size_t k = nv * V + t; k < n; k += nt)
       dst[k] = Traits<TD>::from_acc((typename Traits<TD>::A)Traits<TS>::to_acc(SRC_BYPASS ? ld_bypass(src + k) : src[k]));
@@ -399,6 +418,72 @@ __device__ __forceinline__ void move_tile(TD* dst, const TS* src, size_t n, int 
   Mover<TS, TD, SRC_BYPASS>::run(dst, src, n, t, nt);
 }
 
+// ---------------------------------------------------------------------------------------------
+// 1-byte element types.  The accumulator domain of int8 / uint8 is the 8-bit type itself (SUM and PROD wrap, like the
+// C arithmetic of the reference's CPU path), so the 16 elements of a vector stay packed four to a register and are folded
+// with per-byte SIMD arithmetic: same bits as 16 scalar accumulators, 4 registers instead of 16.
+// ---------------------------------------------------------------------------------------------
+template <int OP, bool SIGNED>
+__device__ __forceinline__ uint32_t red_bytes4(uint32_t x, uint32_t y) {
+  if (OP == B200C_SUM) return __vadd4(x, y);
+  if (OP == B200C_MAX) return SIGNED ? __vmaxs4(x, y) : __vmaxu4(x, y);
+  if (OP == B200C_MIN) return SIGNED ? __vmins4(x, y) : __vminu4(x, y);
+  uint32_t r = 0;  // PROD: the low 8 bits of each product (identical for signed and unsigned operands)
+#pragma unroll
+  for (int q = 0; q < 4; q++) r |= ((((x >> (8 * q)) & 0xffu) * ((y >> (8 * q)) & 0xffu)) & 0xffu) << (8 * q);
+  return r;
+}
+template <bool SIGNED>
+__device__ __forceinline__ uint32_t div_bytes4(uint32_t v, int world) {
+  uint32_t r = 0;  // integer AVG: truncating division of every element by the world size
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    int x = SIGNED ? (int)(int8_t)(v >> (8 * q)) : (int)((v >> (8 * q)) & 0xffu);
+    r |= ((uint32_t)(x / world) & 0xffu) << (8 * q);
+  }
+  return r;
+}
+template <int OP, bool SIGNED>
+__device__ __forceinline__ uint4 red_bytes16(uint4 x, uint4 y) {
+  return make_uint4(red_bytes4<OP, SIGNED>(x.x, y.x), red_bytes4<OP, SIGNED>(x.y, y.y), red_bytes4<OP, SIGNED>(x.z, y.z),
+                    red_bytes4<OP, SIGNED>(x.w, y.w));
+}
+template <typename T, int OP, int WT>
+__device__ __forceinline__ void reduce_vectors_bytes(const CollArgs& a, const T* src0, size_t src_stride, int own_idx,
+                                                     const T* own, T* dst_w, T* dst_i, size_t nv) {
+  constexpr bool SG = (T)(-1) < (T)0;
+  const int W = WT > 0 ? WT : a.c.world;
+  for (size_t i = threadIdx.x; i < nv; i += kThreads) {
+    const uint4 ownv = reinterpret_cast<const uint4*>(own)[i];
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    if (WT > 0) {
+      constexpr int B = WT < 4 ? (WT > 0 ? WT : 1) : 4;
+#pragma unroll
+      for (int s0 = 0; s0 < WT; s0 += B) {
+        uint4 raw[B];
+#pragma unroll
+        for (int k = 0; k < B; k++)
+          raw[k] = ld_bypass16_if(reinterpret_cast<const uint4*>(src0 + (size_t)(s0 + k) * src_stride + i * 16), s0 + k != own_idx);
+#pragma unroll
+        for (int k = 0; k < B; k++) {
+          const uint4 x = (s0 + k == own_idx) ? ownv : raw[k];
+          acc = (s0 + k == 0) ? x : red_bytes16<OP, SG>(acc, x);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int s = 0; s < W; s++) {
+        const uint4 ld = ld_bypass16_if(reinterpret_cast<const uint4*>(src0 + (size_t)s * src_stride + i * 16), s != own_idx);
+        const uint4 x = (s == own_idx) ? ownv : ld;
+        acc = (s == 0) ? x : red_bytes16<OP, SG>(acc, x);
+      }
+    }
+    if (a.has_scale) acc = make_uint4(div_bytes4<SG>(acc.x, W), div_bytes4<SG>(acc.y, W), div_bytes4<SG>(acc.z, W), div_bytes4<SG>(acc.w, W));
+    if (dst_w) reinterpret_cast<uint4*>(dst_w)[i] = acc;
+    if (dst_i) reinterpret_cast<uint4*>(dst_i)[i] = acc;
+  }
+}
+
 // Reduce `world` sources in rank order into up to two destinations.
 //   src0 + s * src_stride points at rank s's contribution (TW, staging -> bypass loads) except
 //   s == own_idx which is `own` (TI, user memory, rounded through TW so every rank's contribution is
@@ -414,7 +499,14 @@ __device__ __forceinline__ void reduce_vectors(const CollArgs& a, const TW* src0
   constexpr int V = 16 / sizeof(TW);
   constexpr int VI = 16 / sizeof(TI);
   const int W = WT > 0 ? WT : a.c.world;
+  if constexpr (sizeof(TW) == 1) {
+    reduce_vectors_bytes<TW, OP, WT>(a, src0, src_stride, own_idx, own, dst_w, dst_i, nv);
+  } else
   for (size_t i = threadIdx.x; i < nv; i += kThreads) {
+    // 8-byte elements: an opaque per-iteration copy of the slot stride keeps the compiler from hoisting all W slot
+    // addresses (two registers each) out of the loop, which cost the W = 8 kernels a spill
+    size_t stride_i = src_stride;
+    if (sizeof(TW) == 8) asm volatile("" : "+l"(stride_i));
     A acc[V];
     TI ownv[V];
     {
@@ -436,7 +528,7 @@ __device__ __forceinline__ void reduce_vectors(const CollArgs& a, const TW* src0
         uint4 raw[B];
 #pragma unroll
         for (int k = 0; k < B; k++)
-          raw[k] = ld_bypass16_if(reinterpret_cast<const uint4*>(src0 + (size_t)(s0 + k) * src_stride + i * V), s0 + k != own_idx);
+          raw[k] = ld_bypass16_if(reinterpret_cast<const uint4*>(src0 + (size_t)(s0 + k) * stride_i + i * V), s0 + k != own_idx);
 #pragma unroll
         for (int k = 0; k < B; k++) {
           const int s = s0 + k;
@@ -455,7 +547,7 @@ __device__ __forceinline__ void reduce_vectors(const CollArgs& a, const TW* src0
 #pragma unroll 1
       for (int s = 0; s < W; s++) {
         Pack16<TW> p;
-        p.u = ld_bypass16_if(reinterpret_cast<const uint4*>(src0 + (size_t)s * src_stride + i * V), s != own_idx);
+        p.u = ld_bypass16_if(reinterpret_cast<const uint4*>(src0 + (size_t)s * stride_i + i * V), s != own_idx);
 #pragma unroll
         for (int e = 0; e < V; e++) {
           A x;
@@ -486,24 +578,20 @@ __device__ __forceinline__ void reduce_vectors(const CollArgs& a, const TW* src0
   }
 }
 
-template <typename TI, typename TW, int OP>
+template <typename TI, typename TW, int OP, int WT>
 __device__ __forceinline__ void reduce_tile(const CollArgs& a, const TW* src0, size_t src_stride, int own_idx,
                                             const TI* own, TW* dst_w, TI* dst_i, size_t n) {
   using A = typename Traits<TW>::A;
   constexpr int V = 16 / sizeof(TW);
-  const int W = a.c.world;
+  const int W = WT > 0 ? WT : a.c.world;
   const int t = threadIdx.x;
   static_assert(sizeof(TI) >= sizeof(TW), "wire type must not be wider than the buffer type");
   bool vec = aligned16(own) && (dst_i == nullptr || aligned16(dst_i));
   size_t nv = vec ? n / V : 0;
-  switch (W) {
-    case 2: reduce_vectors<TI, TW, OP, 2>(a, src0, src_stride, own_idx, own, dst_w, dst_i, nv); break;
-    case 4: reduce_vectors<TI, TW, OP, 4>(a, src0, src_stride, own_idx, own, dst_w, dst_i, nv); break;
-    case 8: reduce_vectors<TI, TW, OP, 8>(a, src0, src_stride, own_idx, own, dst_w, dst_i, nv); break;
-    default: reduce_vectors<TI, TW, OP, 0>(a, src0, src_stride, own_idx, own, dst_w, dst_i, nv); break;
-  }
+  reduce_vectors<TI, TW, OP, WT>(a, src0, src_stride, own_idx, own, dst_w, dst_i, nv);
   for (size_t k = nv * V + t; k < n; k += kThreads) {
     A acc = A();
+#pragma unroll 1
     for (int s = 0; s < W; s++) {
       A x;
       if (s == own_idx) x = Traits<TW>::to_acc(Traits<TW>::from_acc((A)Traits<TI>::to_acc(own[k])));

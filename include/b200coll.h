@@ -105,8 +105,8 @@ typedef struct {
   uint32_t nvls_lanes;         /* lane kernel: lanes (each 1 switch CTA + (max_blocks / lanes - 1 <= 7) copy CTAs) */
   uint64_t lane_granule_bytes; /* lane kernel: bytes of one rank chunk's granule per round (multiple of 8 KiB) */
   uint64_t nvls_lanes_min_bytes; /* AUTO: staged NVLS messages >= this use the lane kernel (0 = never) */
-  uint32_t nvls_unroll;        /* multimem.ld_reduce vectors in flight per thread: 4 or 8 */
-  uint32_t rounds_order;       /* round-pipelined kernel: 1 = copy round q-1 out before the switch stage of round q */
+  uint32_t nvls_unroll;        /* reserved (ignored): round-2 experiment, 8 instead of 4 multimem vectors in flight - no gain, removed */
+  uint32_t rounds_order;       /* reserved (ignored): round-2 experiment, copy-out before the switch stage - slower, removed */
   uint64_t nvls_streams_min_bytes; /* AUTO: staged NVLS messages >= this use the multi-stream pipeline (0 = never) */
   uint64_t nvls_streams_piece_bytes; /* bytes (on the wire) per pipeline piece; at least 3 pieces must fit 2 * staging_bytes */
 } b200c_config_t;

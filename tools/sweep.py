@@ -65,6 +65,7 @@ def main():
     ap.add_argument("--variants", default="", help="extra communicators with config overrides, timed on one algorithm each: "
                     "'label:algo:key=val,key=val;label2:algo2:...' e.g. 'sym64:nvls_sym:nvls_blocks=64;r16:nvls_pipe:granule_bytes=16384'")
     ap.add_argument("--iters-scale", type=float, default=1.0)
+    ap.add_argument("--wire", default="", choices=["", "bf16", "f16"], help="f32 buffers with a 16-bit wire type: the fused gradient-mean call (allreduce_scaled)")
     a = ap.parse_args()
     global PER_ITER
     PER_ITER = a.per_iter
@@ -97,6 +98,14 @@ def main():
     out = {"world": world, "dtype": a.dtype, "multicast": bool(comm.multicast), "nccl_version": ".".join(map(str, torch.cuda.nccl.version())),
            "max_blocks": comm.config.max_blocks, "rows": []}
     k = 2 * (world - 1) / world
+    wire_nat = {"": None, "bf16": N.BFLOAT16, "f16": N.FLOAT16}[a.wire]
+
+    def ar(cx, b, algo):
+        if wire_nat is None:
+            cx.allreduce(b.data_ptr(), b.data_ptr(), n, nat, N.SUM, algo)
+        else:
+            cx.allreduce_scaled(b.data_ptr(), b.data_ptr(), n, nat, wire_nat, 1.0 / world, algo)
+
     for op in a.ops.split(","):
         for size in sizes:
             n = size // esz
@@ -114,7 +123,7 @@ def main():
                         vb = [cx.symmetric_tensor((n,), dtype)]
                         us = timeit(lambda b: cx.allreduce(b.data_ptr(), b.data_ptr(), n, nat, N.SUM, N.ALGO_NVLS), vb, iters, world)
                     else:
-                        us = timeit(lambda b: cx.allreduce(b.data_ptr(), b.data_ptr(), n, nat, N.SUM, algos[algo_name]), bufs, iters, world)
+                        us = timeit(lambda b: ar(cx, b, algos[algo_name]), bufs, iters, world)
                     row[label + "_us"] = round(us, 2)
                     row[label + "_busbw"] = round(size / us / 1e3 * k, 1)
                 for name in [x for x in a.algos.split(",") if x]:
@@ -128,7 +137,7 @@ def main():
                         sb = [comm.symmetric_tensor((n,), dtype)]
                         us = timeit(lambda b: comm.allreduce(b.data_ptr(), b.data_ptr(), n, nat, N.SUM, N.ALGO_NVLS), sb, iters, world)
                     else:
-                        us = timeit(lambda b: comm.allreduce(b.data_ptr(), b.data_ptr(), n, nat, N.SUM, algos[name]), bufs, iters, world)
+                        us = timeit(lambda b: ar(comm, b, algos[name]), bufs, iters, world)
                     row[name + "_us"] = round(us, 2)
                     row[name + "_busbw"] = round(size / us / 1e3 * k, 1)
                     if PER_ITER:
