@@ -360,7 +360,9 @@ __device__ __forceinline__ void convert_tile(TD* __restrict__ dst, const TS* __r
   if (aligned16(dst) && aligned16(src)) {
     size_t nv = n / V;
     constexpr int NS = V / VS, ND = V / VD;   // 16-byte loads / stores per vector step
+#if B200C_CONVERT_UNROLL > 1
     constexpr int U = B200C_CONVERT_UNROLL;   // vector steps in flight per thread
+#endif
     auto convert_store = [&](const uint4* raw, size_t i) {
       TD dv[V];
 #pragma unroll
@@ -380,7 +382,7 @@ __device__ __forceinline__ void convert_tile(TD* __restrict__ dst, const TS* __r
       }
     };
     size_t i = t;
-    if constexpr (U > 1)
+#if B200C_CONVERT_UNROLL > 1
     for (; i + (size_t)(U - 1) * nt < nv; i += (size_t)U * nt) {
       uint4 raw[U][NS];
 #pragma unroll
@@ -392,6 +394,7 @@ __device__ __forceinline__ void convert_tile(TD* __restrict__ dst, const TS* __r
 #pragma unroll
       for (int u = 0; u < U; u++) convert_store(raw[u], i + (size_t)u * nt);
     }
+#endif
     for (; i < nv; i += nt) {
       uint4 raw[NS];
       const uint4* s = reinterpret_cast<const uint4*>(src + i * V);
