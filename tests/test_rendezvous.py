@@ -157,3 +157,45 @@ def test_fd_server_authenticates_requests():
         server.close()
         os.close(r)
         os.close(w)
+
+
+def test_ray_internal_kv_store_against_a_stand_in(monkeypatch):
+    """RayKVStore (the store default_store() picks inside Ray — the channel the reference's gloo rendezvous uses,
+    collective.py:93-110) against an in-process stand-in for ray.experimental.internal_kv: Ray is not installed here."""
+    import sys
+    import types
+
+    table = {}
+    kv = types.ModuleType("ray.experimental.internal_kv")
+    kv._internal_kv_put = lambda k, v, overwrite=True: table.__setitem__(k, v)
+    kv._internal_kv_get = lambda k: table.get(k)
+    kv._internal_kv_del = lambda k: table.pop(k)
+    ray = types.ModuleType("ray")
+    ray.is_initialized = lambda: True
+    ray.experimental = types.ModuleType("ray.experimental")
+    ray.experimental.internal_kv = kv
+    for name, mod in (("ray", ray), ("ray.experimental", ray.experimental), ("ray.experimental.internal_kv", kv)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    monkeypatch.delenv("B200COLL_STORE", raising=False)
+    s = R.default_store()
+    assert isinstance(s, R.RayKVStore)
+    s.set("b200coll/g/0/addr/1", b"abc")
+    assert s.get("b200coll/g/0/addr/1", 1) == b"abc" and table == {"b200coll/g/0/addr/1": b"abc"}
+    threading.Timer(0.05, lambda: s.set("late", b"v")).start()
+    assert s.get("late", 5) == b"v"
+    s.delete("late")
+    s.delete("late")   # deleting a missing key is not an error
+    with pytest.raises(R.RendezvousTimeout):
+        s.get("late", 0.05)
+    # the epoch agreement and a two-rank key exchange run over it like over any other store
+    out = {}
+
+    def rank(r):
+        out[r] = R._agree_on_epoch(s, "b200coll/kvtest", r, 5)
+
+    ts = [threading.Thread(target=rank, args=(r,)) for r in (0, 1)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert out[0] == out[1] and out[0]
