@@ -93,3 +93,26 @@ def test_other_collectives(world):
     world.run(lambda r, c: c.barrier())
     torch.cuda.synchronize()
     world.check()
+
+
+@pytest.mark.parametrize("W", [2, 8])
+def test_signed_bytes_every_op_at_the_compiled_world_sizes(W):
+    """int8 MAX / MIN / PROD / AVG through the packed per-byte reduce in the kernels compiled for a fixed world size
+    (the main loopback suite pins int8 SUM and uint8 for every op)."""
+    from ant_ray_b200.loopback import LoopbackWorld
+
+    w = LoopbackWorld(W, device=0, key=f"lb-i8-{W}", staging_bytes=1 << 20, timeout_ms=20000)
+    try:
+        for algo in (N.ALGO_LL, N.ALGO_ONESHOT, N.ALGO_TWOSHOT):
+            for opname, (nat, orc) in OPS.items():
+                for n in (7, 5000, 30_011):
+                    ins = [make_input(torch.int8, n, r, opname) for r in range(W)]
+                    dev = [t.cuda() for t in ins]
+                    w.run(lambda r, c: c.allreduce(dev[r].data_ptr(), dev[r].data_ptr(), n, N.INT8, nat, algo))
+                    torch.cuda.synchronize()
+                    w.check()
+                    want = O.allreduce(ins, orc)
+                    for r in range(W):
+                        assert_equal_bits(dev[r], want, f"W={W} int8 n={n} op={opname} algo={algo} rank={r}")
+    finally:
+        w.destroy()
