@@ -19,7 +19,7 @@ the resolver installed by `experimental_collective.set_runtime`.
 import logging
 import threading
 import uuid
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 from . import experimental_collective as _xc
 
